@@ -1,0 +1,168 @@
+/*
+ * jsfe.h -- C ABI of the B200-native stereo front-end (libjsfe.so).
+ *
+ * This is the drop-in boundary for the reference's per-frame hot path.  The reference
+ * (ashishkumar822/Jetson-SLAM, paths relative to its root) has no plugin/FFI layer: its SLAM core
+ * includes five C++ entities directly.  Each entry point below names the reference interface it
+ * replaces; compat/ re-implements those C++ headers as thin shims over this ABI.
+ *
+ *   extern "C", plain pointers and sizes, no C++/torch types.  Every call returns 0 (JSFE_OK) or a
+ *   negative jsfe_status; jsfe_last_error() gives a thread-local message.  There is NO CPU fallback:
+ *   without a CUDA device jsfe_create fails with JSFE_ERR_CUDA.
+ *
+ * Model: a handle owns `max_images` image SLOTS on one GPU.  A slot is one eye: its level-0 image,
+ * its pyramid, its keypoints/descriptors.  Stereo pair p uses slot 2p (left) and 2p+1 (right).
+ * The reference's "one ORB_GPU per eye" maps to a handle with max_images = 1 (compat/) and the
+ * batched B200 path to one handle with max_images = 2 * pairs.  All device memory is allocated in
+ * jsfe_create; nothing is allocated on the per-frame path.  A handle is single-threaded; distinct
+ * handles may be driven concurrently from distinct host threads (the reference does this for L/R,
+ * src/Frame.cpp:107-110).  Work is enqueued on the caller's CUDA stream (cudaStream_t passed as
+ * void*; NULL = the legacy default stream); only the jsfe_get_* / jsfe_download_* calls synchronise.
+ */
+#ifndef JSFE_H
+#define JSFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSFE_MAX_LEVELS 16
+#define JSFE_BORDER 20 /* BORDER_SKIP, include/cuda/orb_gpu.hpp:17 */
+
+typedef enum jsfe_status {
+    JSFE_OK = 0,
+    JSFE_ERR_INVALID = -1, /* bad argument / configuration                 */
+    JSFE_ERR_CUDA = -2,    /* CUDA runtime error (message has the details) */
+    JSFE_ERR_CAPACITY = -3 /* more images/pairs than the handle's slots    */
+} jsfe_status;
+
+/* Mirrors the 15 constructor parameters of Jetson_SLAM::ORBExtractor (include/ORBextractor.h:25-35)
+ * = orb_cuda::ORB_GPU (include/cuda/orb_gpu.hpp:26-35), plus device/slot sizing.
+ * The reference loads its mask from a file path (src/cuda/orb_gpu.cpp:64-91); here the caller
+ * passes the level-0 mask bytes (NULL = all 255); levels are nearest-neighbour resized and
+ * thresholded at 10 exactly as the reference does. */
+typedef struct jsfe_config {
+    int32_t height, width;
+    int32_t n_levels;
+    float scale_factor;
+    int32_t fast_n_min, fast_n_max;
+    int32_t th_fast_min, th_fast_max; /* th_fast_min is accepted and ignored, as in the reference (orb_gpu.cpp:42-47) */
+    int32_t tile_h, tile_w;
+    int32_t fixed_multi_scale_tile_size;
+    int32_t apply_nms_ms;    /* effective only for n_levels > 1 (orb_gpu.cpp:37) */
+    int32_t nms_ms_mode_gpu; /* 1: dense-volume rule (deterministic two-phase), 0: bucket rule (orb_FAST_apply_NMS_MS.cpp) */
+    const uint8_t* mask;     /* host pointer, height x mask_pitch, or NULL */
+    int64_t mask_pitch;
+    int32_t device_id;
+    int32_t max_images; /* image slots; >= 1 */
+} jsfe_config;
+
+typedef struct jsfe_handle jsfe_handle;
+
+/* Per-level geometry (orb_gpu.cpp:49-62, 224-258, 305-327). */
+typedef struct jsfe_level_info {
+    int32_t height, width;
+    int32_t pitch; /* bytes per row of the device level image (multiple of 16) */
+    int32_t tile_h, tile_w, n_tile_h, n_tile_w;
+    int32_t cell_offset; /* level_offset_[i] */
+    float scale, inv_scale;
+} jsfe_level_info;
+
+/* Device-side view of one slot's results (all pointers are device pointers owned by the handle).
+ * kps: 6 planes [x | y | score | angle_deg(f32 bits) | octave | size], plane stride = capacity.
+ * Same plane order as ORB_GPU::extract's out_keypoints (orb_gpu.cpp:784-816); the reference packs
+ * planes with stride N, jsfe_pack_keypoints produces exactly that layout. */
+typedef struct jsfe_slot_view {
+    const int32_t* n_keypoints;  /* 1 int                           */
+    const int32_t* n_per_level;  /* n_levels ints                   */
+    const int32_t* kps;          /* 6 * capacity                    */
+    const uint8_t* desc;         /* 32 * capacity                   */
+    const float* u_right;        /* capacity (left slots, after jsfe_stereo_match) */
+    const float* depth;          /* capacity                        */
+    const int32_t* best_idx_r;   /* capacity: Hamming arg-min right index or -1    */
+    const int32_t* best_dist;    /* capacity: its distance or TH_HIGH              */
+    int32_t capacity;
+} jsfe_slot_view;
+
+const char* jsfe_last_error(void);
+
+/* ---- lifetime: replaces ORBExtractor::ORBExtractor / ~ORBExtractor (src/ORBextractor.cpp:27-95)
+ *      and ORB_GPU::ORB_GPU / ~ORB_GPU (src/cuda/orb_gpu.cpp:22-453). */
+int jsfe_create(const jsfe_config* cfg, jsfe_handle** out);
+int jsfe_destroy(jsfe_handle* h);
+
+/* ---- geometry: replaces ORBExtractor::get_levels / get_scale_factors / get_inverse_scale_factors
+ *      (include/ORBextractor.h:44-72) and the public ORB_GPU::height_/width_ (orb_gpu.hpp:242-243). */
+int jsfe_max_keypoints(const jsfe_handle* h); /* max_kp_count_ (orb_gpu.cpp:321) = per-slot capacity */
+int jsfe_num_levels(const jsfe_handle* h);
+int jsfe_get_level_info(const jsfe_handle* h, int level, jsfe_level_info* out);
+
+/* ---- input: replaces the cudaMemcpy2D upload at orb_gpu.cpp:497.
+ * Copies n images into slots [first_slot, first_slot+n).  src may be host (pinned for async) or
+ * device memory; row_pitch / image_stride in bytes.  Asynchronous on `stream`. */
+int jsfe_set_images(jsfe_handle* h, int first_slot, int n, const uint8_t* src, int64_t row_pitch,
+                    int64_t image_stride, int src_is_device, void* stream);
+/* Zero-copy alternative: device pointer + pitch of a slot's level-0 image, for producers that write
+ * frames straight into the slot (capture DMA, rectification kernel). */
+int jsfe_slot_image(jsfe_handle* h, int slot, uint8_t** dev_ptr, int64_t* pitch);
+
+/* ---- extraction: replaces ORBExtractor::extract (src/ORBextractor.cpp:97-105) ->
+ *      ORB_GPU::extract (src/cuda/orb_gpu.cpp:489-841) for slots [first_slot, first_slot+n):
+ *      pyramid, FAST score, per-cell NMS arg-max, optional cross-scale NMS, ordered compaction,
+ *      IC angle, 7x7 blur, rBRIEF, output packing.  Asynchronous on `stream`. */
+int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream);
+
+/* ---- stereo: replaces ORB_GPU::ORB_compute_stereo_match (include/cuda/orb_gpu.hpp:218-229,
+ *      src/cuda/orb_stereo_match.cu:105-580) as called by Frame::ComputeStereoMatches
+ *      (src/Frame.cpp:780-803) for pairs [first_pair, first_pair+n): left = slot 2p, right = 2p+1.
+ *      mb is explicit (the reference reads Frame::mb before assigning it; benchmarks use mbf/fx).
+ *      Results land in the LEFT slot's u_right/depth/best_idx_r/best_dist.  Asynchronous. */
+int jsfe_stereo_match(jsfe_handle* h, int first_pair, int n, int th_high, int th_low, float mb, float mbf,
+                      void* stream);
+
+/* ---- results */
+int jsfe_slot_view_get(const jsfe_handle* h, int slot, jsfe_slot_view* out);
+/* Level image left on the device by the last extract: replaces the public ORB_GPU::image_
+ * (orb_gpu.hpp:247) that Frame::ComputeStereoMatches hands to the matcher. */
+int jsfe_level_image(const jsfe_handle* h, int slot, int level, const uint8_t** dev_ptr, int32_t* height,
+                     int32_t* width, int64_t* pitch);
+/* Pack a slot's keypoints the way the reference returns them (6 planes, stride N; descriptors 32N)
+ * into CALLER-owned device buffers (the compat SyncedMem): orb_gpu.cpp:784-831.  *n_out receives N
+ * (this call synchronises `stream` to learn N). dst_kps needs 6*capacity ints, dst_desc 32*capacity. */
+int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out,
+                        void* stream);
+/* Host copies (synchronise `stream`).  kps_host: 6*N ints with stride N (reference layout), desc_host 32*N;
+ * either may be NULL.  Capacity of the host buffers must be jsfe_max_keypoints(). */
+int jsfe_get_keypoints(jsfe_handle* h, int slot, int32_t* kps_host, uint8_t* desc_host, int32_t* n_out, void* stream);
+int jsfe_get_stereo(jsfe_handle* h, int pair, float* u_right_host, float* depth_host, int32_t* best_idx_r_host,
+                    int32_t* best_dist_host, int32_t* n_left_out, void* stream);
+
+/* Bulk D2H of n slots' result slabs into the handle's pinned staging area (one async copy per
+ * array kind, then one synchronise): the per-step readback of the end-to-end path.
+ * After it returns, jsfe_host_results gives host pointers into the staging area. */
+typedef struct jsfe_host_results {
+    const int32_t* n_keypoints; /* [n]                      */
+    const int32_t* kps;         /* [n][6][capacity]         */
+    const uint8_t* desc;        /* [n][capacity][32]        */
+    const float* u_right;       /* [n][capacity] (left slots meaningful) */
+    const float* depth;         /* [n][capacity]            */
+    int32_t capacity;
+    int64_t bytes; /* bytes copied D2H by the last jsfe_download_results */
+} jsfe_host_results;
+int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_results* out, void* stream);
+
+/* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
+int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
+int jsfe_debug_cells(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score /* capacity each */);
+int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score, int32_t* level,
+                               float* angle_rad /* capacity each, first N valid */);
+/* number of kernels the library has launched since creation (bench.py's gpu_launches) */
+int64_t jsfe_launch_count(const jsfe_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSFE_H */

@@ -1,0 +1,130 @@
+/*
+ * jsfe_oracle.h -- CPU restatement of the Jetson-SLAM stereo front-end.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped product (jetson_slam_b200/,
+ * include/jsfe.h, libjsfe.so) may include, link or call this code: it exists so
+ * that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference leg can check (and time beside) the CUDA path.
+ *
+ * It restates, stage by stage, what the reference's hot path computes
+ * (reference = ashishkumar822/Jetson-SLAM, paths relative to /root/reference):
+ *   geometry/tables  src/cuda/orb_gpu.cpp:22-441
+ *   pyramid          src/cuda/orb_pyramid.cu:18-68
+ *   FAST score       src/cuda/orb_FAST_compute_score.cu:1412-1560
+ *   cell NMS/argmax  src/cuda/orb_FAST_apply_NMS_G.cu:1178-1483
+ *   cross-scale NMS  src/cuda/orb_FAST_apply_NMS_MS.cu:18-467, orb_FAST_apply_NMS_MS.cpp:15-122
+ *   compaction       src/cuda/orb_FAST_obtain_keypoints.cpp:12-56
+ *   orientation      src/cuda/orb_FAST_orientation.cu:17-65
+ *   7x7 blur         src/cuda/orb_gaussian.cu:21-138
+ *   rBRIEF           src/cuda/orb_descriptor.cu:12-69 (+ OpenCV bit_pattern_31_)
+ *   output packing   src/cuda/orb_copy_output.cu:12-45
+ *   stereo match     src/cuda/orb_stereo_match.cu:28-580
+ *
+ * Parity pin: the reference ships NO tests, fixtures or golden vectors for this
+ * path.  This oracle is pinned against the reference's own
+ * src/cuda compiled unmodified for sm_100a (oracle/ref_build -> oracle/_ref)
+ * and run on a B200; the resulting vectors are committed under tests/golden/.
+ * Until tests/golden/ref_*.npz exist the status is "parity unpinned".
+ */
+#ifndef JSFE_ORACLE_H
+#define JSFE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_LEVELS 16
+#define ORC_BORDER 20 /* BORDER_SKIP, include/cuda/orb_gpu.hpp:17 */
+
+typedef struct orc_config {
+    int32_t height, width;
+    int32_t n_levels;
+    float scale_factor;
+    int32_t fast_n_min, fast_n_max;
+    int32_t th_fast_min, th_fast_max; /* th_fast_min is ignored, as in the reference (orb_gpu.cpp:42-47) */
+    int32_t tile_h, tile_w;
+    int32_t fixed_multi_scale_tile_size;
+    int32_t apply_nms_ms;    /* effective only when n_levels > 1 (orb_gpu.cpp:37) */
+    int32_t nms_ms_mode_gpu; /* 1: dense s0-volume variant (two-phase deterministic), 0: CPU bucket variant */
+} orc_config;
+
+typedef struct orc_ctx orc_ctx;
+
+/* mask: NULL (all 255) or height*width bytes (level-0 mask; levels are NN-resized + thresholded >10). */
+orc_ctx* orc_create(const orc_config* cfg, const uint8_t* mask);
+void orc_destroy(orc_ctx* c);
+
+int orc_max_kp(const orc_ctx* c);
+int orc_n_levels(const orc_ctx* c);
+/* per level: h,w,tile_h,tile_w,n_tile_h,n_tile_w,level_offset  (7 ints per level) */
+void orc_level_geometry(const orc_ctx* c, int32_t* out7);
+void orc_scales(const orc_ctx* c, float* scale, float* inv_scale);
+const uint8_t* orc_lut(const orc_ctx* c);       /* 65536 bytes, [0xFFFF] = 0 */
+const int32_t* orc_umax(const orc_ctx* c);      /* 16 */
+const float* orc_gauss(const orc_ctx* c);       /* 49 */
+const int8_t* orc_pattern_x(const orc_ctx* c);  /* 512 */
+const int8_t* orc_pattern_y(const orc_ctx* c);  /* 512 */
+/* column priority permutation of the NMS-G smem tree for a given tile_w: rank[j] (0 = wins ties) */
+void orc_column_rank(int tile_w, int32_t* rank);
+
+/*
+ * Full extraction of one eye.  image: height*width contiguous u8.
+ * kps_soa: 6*N int32 planes [x|y|score|angle(f32 bits)|octave|size] laid out with stride N (= return value),
+ * exactly as ORB_GPU::extract leaves `out_keypoints` (orb_gpu.cpp:784-816).  Caller provides 6*max_kp ints.
+ * desc: 32*N bytes.  Returns N (total keypoints).
+ */
+int orc_extract(orc_ctx* c, const uint8_t* image, int32_t* kps_soa, uint8_t* desc);
+
+/* stage accessors (valid after orc_extract) */
+const uint8_t* orc_level_image(const orc_ctx* c, int level);
+const uint8_t* orc_level_blur(const orc_ctx* c, int level);
+const int32_t* orc_level_score(const orc_ctx* c, int level);
+/* per-cell candidates before compaction (max_kp each, level_offset-indexed) */
+const int32_t* orc_cell_x(const orc_ctx* c);
+const int32_t* orc_cell_y(const orc_ctx* c);
+const int32_t* orc_cell_score(const orc_ctx* c);
+/* compacted level-coordinate keypoints: n per level, arrays indexed level_offset[l]+j */
+const int32_t* orc_n_keypoints(const orc_ctx* c);
+const int32_t* orc_kp_x(const orc_ctx* c);
+const int32_t* orc_kp_y(const orc_ctx* c);
+const int32_t* orc_kp_score(const orc_ctx* c);
+const float* orc_kp_angle(const orc_ctx* c);
+
+/* individual stages, exposed for unit tests */
+void orc_stage_pyramid(orc_ctx* c, const uint8_t* image);
+void orc_stage_fast(orc_ctx* c);
+void orc_stage_cells(orc_ctx* c);
+void orc_stage_nms_ms(orc_ctx* c);
+void orc_stage_compact(orc_ctx* c);
+void orc_stage_orient(orc_ctx* c);
+void orc_stage_blur(orc_ctx* c);
+void orc_stage_describe(orc_ctx* c);
+
+/* libdevice transcriptions (CUDA 12.9 libdevice, fast path |x| < 105615) */
+float orc_atan2f(float y, float x);
+float orc_cosf(float x);
+float orc_sinf(float x);
+
+/*
+ * Stereo match (orb_stereo_match.cu:105-580).  cl / cr hold the left / right pyramids of the last
+ * orc_extract.  kps_* are the 6-plane SoAs with stride n_*.  Outputs u_right[n_left], depth[n_left]
+ * (-1 = no match).  Optional debug outputs (may be NULL): best_idx_r[n_left] (Hamming arg-min right
+ * index or -1), best_dist[n_left] (Hamming distance or th_high).
+ * Returns the number of left keypoints that keep a depth.
+ */
+int orc_stereo_match(const orc_ctx* cl, const orc_ctx* cr, int th_high, int th_low, float mb, float mbf,
+                     int n_left, const int32_t* kps_left, const uint8_t* desc_left,
+                     int n_right, const int32_t* kps_right, const uint8_t* desc_right,
+                     float* u_right, float* depth, int32_t* best_idx_r, int32_t* best_dist);
+
+/* Convenience for the CPU baseline: extract both eyes (optionally on 2 threads) + match. Returns n_left. */
+int orc_stereo_pair(orc_ctx* cl, orc_ctx* cr, const uint8_t* img_l, const uint8_t* img_r,
+                    float mb, float mbf, int32_t* kps_l, uint8_t* desc_l, int32_t* n_r_out,
+                    int32_t* kps_r, uint8_t* desc_r, float* u_right, float* depth, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
