@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- stereo front-end throughput on B200 (BASELINE.json metric: stereo pairs/s @1241x376, ~2000 feat).
+
+  python bench.py --gpus N --steps K --warmup W          our CUDA path (libjsfe.so through the C ABI)
+  python bench.py --impl reference ...                    the CPU restatement of the reference's path on the host cores
+
+One "step" = one pass of the whole hot path (pyramid -> FAST/NMS -> compaction -> angle+blur+rBRIEF for both eyes,
+then the left<->right Hamming + SAD stereo match) over a batch of `--pairs` synthetic stereo pairs per GPU.
+`value`  : pairs/s with the level-0 images already resident in HBM (the handle's image slots).
+`e2e`    : the same metric through the public API with HOST buffers: pinned H2D of every image and the D2H of
+           every result slab inside the timed region.
+Inputs: 2*pairs images of 1241x376 u8 per GPU per step = 150 MB at the default 160 pairs -> larger than the 126 MB L2,
+so no L2 flush is needed between iterations (config.l2: "inputs>L2").
+Timing: CUDA events on the launching stream, bracketed by barrier + synchronize, max over ranks.
+Multi-GPU: pairs are independent -> one process per GPU, no data-path collective (weak scaling); `--gather` adds the
+NCCL gather of result slabs to rank 0 that a batch consumer would request.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stereo front-end pairs/sec @1241x376, ~2000 feat (keypoints bit-exact vs ref)"
+UNIT = "pairs/s"
+
+
+def bytes_per_pair(levels_hw, cap):
+    """compulsory traffic of a perfectly fused implementation, per stereo pair.
+    bytes_pair = 2*[P0 + 2*sum(P_i>=1) + N*(24+32)] + N*(64 + 2*11*21 + 8)"""
+    p0 = levels_hw[0][0] * levels_hw[0][1]
+    prest = sum(h * w for h, w in levels_hw[1:])
+    return 2 * (p0 + 2 * prest + cap * 56) + cap * (64 + 462 + 8)
+
+
+def kernel_algorithmic_bytes(levels_hw, cap, n_mean):
+    """Per-IMAGE (per-pair for the stereo kernels) algorithmic bytes of each kernel."""
+    p0 = levels_hw[0][0] * levels_hw[0][1]
+    prest = sum(h * w for h, w in levels_hw[1:])
+    return {
+        "k_pyramid": p0 + prest,                       # read L0 once, write every resampled level once
+        "k_fast_cells": p0 + prest + 12 * cap,         # read every level once, write (x,y,score) per cell
+        "k_compact": 12 * cap + 16 * n_mean,           # read cells, write compacted (x,y,score,level)
+        "k_orient_desc": n_mean * (43 * 43 + 16 + 56 + 4),  # read the 43x43 patch + kp, write SoA 24B + desc 32B + angle
+        "k_stereo_match": n_mean * (64 + 462 + 8),     # per PAIR: 2 descriptors, two 11x21 strips, uRight+depth
+        "k_stereo_outlier": n_mean * 4,                # per PAIR
+        "k_nms_ms": 12 * cap,
+    }
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml, fallback nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture summary (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_pairs_per_s(cfg, pairs_imgs, threads, pairs_total):
+    """Time the oracle (CPU restatement of the reference's path) on `threads` host threads, one stereo pair per task."""
+    from oracle import oracle as orc
+    import ctypes as C
+    kw = cfg.extractor_kwargs()
+    ctxs = [(orc.Oracle(**kw), orc.Oracle(**kw)) for _ in range(threads)]
+    cap = ctxs[0][0].max_kp
+    bufs = [dict(kl=np.zeros(6 * cap, np.int32), dl=np.zeros(32 * cap, np.uint8), kr=np.zeros(6 * cap, np.int32),
+                 dr=np.zeros(32 * cap, np.uint8), ur=np.zeros(cap, np.float32), dp=np.zeros(cap, np.float32),
+                 nr=C.c_int32()) for _ in range(threads)]
+    L = orc.lib()
+    counter = {"next": 0}
+    lock = threading.Lock()
+
+    def worker(t):
+        ol, orr = ctxs[t]
+        b = bufs[t]
+        while True:
+            with lock:
+                i = counter["next"]
+                counter["next"] += 1
+            if i >= pairs_total:
+                return
+            il, ir = pairs_imgs[i % len(pairs_imgs)]
+            L.orc_stereo_pair(ol._h, orr._h, il.ctypes.data, ir.ctypes.data, cfg.mb, cfg.mbf, b["kl"].ctypes.data,
+                              b["dl"].ctypes.data, C.byref(b["nr"]), b["kr"].ctypes.data, b["dr"].ctypes.data,
+                              b["ur"].ctypes.data, b["dp"].ctypes.data, 1)
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return pairs_total / dt, dt
+
+
+def ref_cuda_pairs_per_s(cfg, pair, iters=40):
+    """The reference's own src/cuda (compiled unmodified for sm_100a, oracle/_ref) driven like Frame::Frame does."""
+    try:
+        from oracle import ref
+        if not ref.available():
+            return None
+        kw = cfg.extractor_kwargs()
+        rl, rr = ref.RefEye(**kw), ref.RefEye(**kw)
+        ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, 5, True)
+        out = {}
+        for two in (True, False):
+            dt = ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, iters, two)
+            out["two_threads" if two else "one_thread"] = iters / dt
+        rl.close()
+        rr.close()
+        return {"value": max(out.values()), "unit": UNIT, "detail": out, "iters": iters,
+                "how": "ORB_GPU::extract x2 (host images, its own H2D/D2H) + ORB_compute_stereo_match, wall clock"}
+    except Exception as e:  # the reference library is optional colour, never the measured product
+        return {"unavailable": repr(e)[:200]}
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from jetson_slam_b200 import synth
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, args.cpu_threads or cores))
+    imgs = [synth.stereo_pair(cfg.height, cfg.width, s) for s in range(4)]
+    per_step = threads  # bounded sample: one pair per host thread per step
+    for _ in range(args.warmup):
+        cpu_pairs_per_s(cfg, imgs, threads, max(1, per_step // 4))
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        v, dt = cpu_pairs_per_s(cfg, imgs, threads, per_step)
+        t_total += dt
+        n_total += per_step
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": cfg.name, "pairs_per_step": per_step, "height": cfg.height, "width": cfg.width,
+                   "n_levels": cfg.n_levels, "tile": cfg.tile_h,
+                   "note": "the reference has no CPU extractor/matcher (SURVEY F2/F3); this arm is the CPU restatement "
+                           "(oracle port) of its CUDA path, one pair per host thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_total} C2 stereo pairs over {args.steps} steps, {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    try:
+        import torch
+        if torch.cuda.is_available():
+            line["ref_cuda"] = ref_cuda_pairs_per_s(cfg, imgs[0])
+    except Exception:
+        pass
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from jetson_slam_b200 import frontend, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = args.pairs
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
+    # distinct synthetic pairs (rank-dependent seeds), cycled over the slots
+    n_distinct = min(B, args.distinct)
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, 1000 * rank + s) for s in range(n_distinct)]
+    host = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for p in range(B):
+        hv[2 * p], hv[2 * p + 1] = pairs[p % n_distinct]
+    stream = torch.cuda.Stream()
+    fe.set_images(hv, 0, stream)
+    stream.synchronize()
+
+    def step_device():
+        fe.extract(0, 2 * B, stream)
+        fe.stereo_match(cfg.mb, cfg.mbf, 0, B, stream=stream)
+
+    def step_e2e():
+        fe.set_images(hv, 0, stream)
+        fe.extract(0, 2 * B, stream)
+        fe.stereo_match(cfg.mb, cfg.mbf, 0, B, stream=stream)
+        return fe.download(0, 2 * B, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = fe.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = fe.launch_count() - l0
+    clocks = sampler.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # e2e: host buffers in, host results out, every step
+    for _ in range(2):
+        step_e2e()
+    t0 = time.perf_counter()
+    ms_e2e = timed(step_e2e, args.steps)
+    wall_e2e = time.perf_counter() - t0
+    res = step_e2e()
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    n_mean = float(res["n"].mean())
+    d2h = int(res["bytes"])
+    matched = int((res["u_right"][0::2] >= 0).sum())
+
+    # per-kernel durations (CUDA events on the launching stream around every launch)
+    fe.profile(True)
+    for _ in range(args.steps):
+        step_device()
+    stream.synchronize()
+    prof = fe.profile_read()
+    fe.profile(False)
+    levels = [(li.height, li.width) for li in fe.levels]
+    alg = kernel_algorithmic_bytes(levels, fe.max_kp, n_mean)
+    per_kernel = {}
+    for k, (tot_ms, cnt) in prof.items():
+        if cnt:
+            units = B if k.startswith("k_stereo") else 2 * B
+            per_kernel[k] = {"ms_per_launch": tot_ms / cnt, "alg_bytes_per_launch": alg[k] * units}
+    total_k = sum(v["ms_per_launch"] for v in per_kernel.values()) or 1.0
+    for v in per_kernel.values():
+        v["share"] = v["ms_per_launch"] / total_k
+        v["gbs"] = v["alg_bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"])
+    peak, peak_src = measured_hbm_peak()
+    bpp = bytes_per_pair(levels, fe.max_kp)
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, args.cpu_threads or 32))
+        sample_pairs = 2 * threads
+        cpu_v, cpu_dt = cpu_pairs_per_s(cfg, pairs[: min(4, len(pairs))], threads, sample_pairs)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": cfg.name, "pairs_per_step_per_gpu": B, "height": cfg.height, "width": cfg.width,
+                       "n_levels": cfg.n_levels, "tile": cfg.tile_h, "max_keypoints_per_eye": fe.max_kp,
+                       "mean_keypoints_per_eye": n_mean, "stereo_matches_per_step": matched,
+                       "distinct_pairs": n_distinct, "l2": "inputs>L2 (%.0f MB of level-0 images per step)" % (2 * B * cfg.height * cfg.width / 1e6),
+                       "parallelism": f"pairs sharded one-batch-per-GPU x{world}, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * cfg.height * cfg.width),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": per_kernel[dom]["gbs"] / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                         "ms_per_launch": per_kernel[dom]["ms_per_launch"], "share_of_step": per_kernel[dom]["share"]},
+            "pipeline_roofline": {"bytes_per_pair": bpp, "achieved": bpp * value / world / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": bpp * value / world / 1e9 / peak},
+            "kernels": per_kernel,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample_pairs} C2 stereo pairs on {threads} threads ({cpu_dt:.1f} s wall)"},
+        }
+        if not args.no_ref_cuda:
+            line["ref_cuda"] = ref_cuda_pairs_per_s(cfg, pairs[0])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--pairs", type=int, default=160, help="stereo pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs cycled over the batch")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    from jetson_slam_b200.configs import CONFIGS
+    cfg = CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

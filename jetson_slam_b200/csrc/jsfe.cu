@@ -1,0 +1,614 @@
+// jsfe.cu -- host side of libjsfe.so: handle, geometry/tables, device arenas, kernel sequencing and
+// the C ABI declared in include/jsfe.h.  No CPU fallback: every compute entry point launches CUDA.
+//
+// Geometry and tables restate src/cuda/orb_gpu.cpp:22-441 of the reference (float32 level scales,
+// truncating level sizes, per-level tile sizes, FAST arc LUT built by the reference's scan procedure,
+// umax, 7x7 sigma=10 weights, OpenCV rBRIEF pattern).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/jsfe.h"
+#include "jsfe_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail(JSFE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+const int kPattern[256 * 4] = {
+#include "orb_pattern_31.inc"
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The reference's smem tree over a tile's columns (orb_FAST_apply_NMS_G.cu:1331-1364), run on slot ids:
+// column j beats column k on equal scores iff the tree returns j when only j and k hold the maximum.
+void column_rank(int tile_w, uint8_t* rank, uint8_t* by_rank) {
+    std::vector<int> val(tile_w), id(tile_w);
+    const int steps = (int)std::ceil(std::log2((float)tile_w));
+    for (int j = 0; j < tile_w; ++j) {
+        int wins = 0;
+        for (int k = 0; k < tile_w; ++k) {
+            if (k == j) continue;
+            for (int q = 0; q < tile_w; ++q) { val[q] = (q == j || q == k); id[q] = q; }
+            int g = (tile_w - 1) / 2 + 1;
+            for (int it = 0; it < steps; ++it) {
+                for (int q = 0; q < g && q < tile_w; ++q)
+                    if (q + g < tile_w && val[q] < val[q + g]) { val[q] = val[q + g]; id[q] = id[q + g]; }
+                g = (g - 1) / 2 + 1;
+            }
+            if (id[0] == j) ++wins;
+        }
+        rank[j] = (uint8_t)(tile_w - 1 - wins);
+    }
+    for (int j = 0; j < tile_w; ++j) by_rank[rank[j]] = (uint8_t)j;
+}
+
+}  // namespace
+
+struct jsfe_handle {
+    jsfe_config cfg;
+    int device = 0;
+    int max_images = 0;
+    jsfe::Params P;       // host copy of the kernel parameter block
+    size_t fast_smem = 0; // dynamic shared memory of k_fast_cells
+    std::vector<void*> dev_allocs;
+    // pinned staging for jsfe_download_results / jsfe_get_*
+    int32_t* h_n = nullptr;
+    int32_t* h_kps = nullptr;
+    uint8_t* h_desc = nullptr;
+    float* h_ur = nullptr;
+    float* h_dp = nullptr;
+    int32_t* h_misc = nullptr;  // cap ints scratch x 4
+    int64_t launches = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(jsfe_handle* h, T** out, size_t count, bool zero = true) {
+    void* ptr = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CU(cudaMalloc(&ptr, bytes));
+    h->dev_allocs.push_back(ptr);
+    if (zero) CU(cudaMemset(ptr, 0, bytes));
+    *out = (T*)ptr;
+    return JSFE_OK;
+}
+
+int check_slots(const jsfe_handle* h, int first, int n) {
+    if (!h) return fail(JSFE_ERR_INVALID, "null handle");
+    if (first < 0 || n < 0 || first + n > h->max_images)
+        return fail(JSFE_ERR_CAPACITY, "slots [%d,%d) exceed the handle's %d image slots", first, first + n, h->max_images);
+    return JSFE_OK;
+}
+
+cudaEvent_t take_event(jsfe_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// RAII span around one kernel launch when profiling is on
+struct StageTimer {
+    jsfe_handle* h; cudaStream_t st; int stage; cudaEvent_t a = nullptr;
+    StageTimer(jsfe_handle* h_, cudaStream_t st_, int stage_) : h(h_), st(st_), stage(stage_) {
+        if (h->profiling) { a = take_event(h); cudaEventRecord(a, st); }
+    }
+    ~StageTimer() {
+        if (a) { cudaEvent_t b = take_event(h); cudaEventRecord(b, st); h->spans.push_back({stage, a, b}); }
+    }
+};
+
+int post_launch(jsfe_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(JSFE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    ++h->launches;
+    return JSFE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jsfe_last_error(void) { return g_err.c_str(); }
+
+int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
+    if (!cfg || !out) return fail(JSFE_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_levels < 1 || cfg->n_levels > JSFE_MAXL) return fail(JSFE_ERR_INVALID, "n_levels must be in [1,%d]", JSFE_MAXL);
+    if (cfg->height < 1 || cfg->width < 1 || cfg->max_images < 1) return fail(JSFE_ERR_INVALID, "bad image size / max_images");
+    if (!(cfg->scale_factor >= 1.0f)) return fail(JSFE_ERR_INVALID, "scale_factor must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(JSFE_ERR_CUDA, "no CUDA device: libjsfe has no CPU fallback");
+    if (cfg->device_id < 0 || cfg->device_id >= ndev) return fail(JSFE_ERR_INVALID, "device_id %d out of range", cfg->device_id);
+    CU(cudaSetDevice(cfg->device_id));
+
+    jsfe_handle* h = new (std::nothrow) jsfe_handle;
+    if (!h) return fail(JSFE_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->cfg.mask = nullptr;
+    h->device = cfg->device_id;
+    h->max_images = cfg->max_images;
+    jsfe::Params& P = h->P;
+    memset(&P, 0, sizeof P);
+    P.L = cfg->n_levels;
+    P.threshold = cfg->th_fast_max;  // the reference overwrites th_FAST_MIN_ and uses th_FAST_MAX only (orb_gpu.cpp:42-47)
+    P.H0 = cfg->height;
+    P.W0 = cfg->width;
+
+    // ---- level geometry (orb_gpu.cpp:49-62, 224-258, 305-327), all float32
+    float scale[JSFE_MAXL], inv[JSFE_MAXL];
+    scale[0] = 1.0f;
+    inv[0] = 1.0f;
+    for (int i = 1; i < P.L; ++i) {
+        scale[i] = cfg->scale_factor * scale[i - 1];
+        inv[i] = 1.0f / scale[i];
+    }
+    int cells = 0, tile_rows = 0, items = 0;
+    size_t smem_max = 0;
+    P.pyr_group_start[0] = 0;
+    P.pyr_group_start[1] = 0;
+    for (int i = 0; i < P.L; ++i) {
+        jsfe::LevelGeom& g = P.lv[i];
+        g.h = i ? (int)((float)cfg->height * inv[i]) : cfg->height;
+        g.w = i ? (int)((float)cfg->width * inv[i]) : cfg->width;
+        if (g.h < 1 || g.w < 1) { delete h; return fail(JSFE_ERR_INVALID, "level %d is empty", i); }
+        g.pitch = (int)align_up(g.w, 16);
+        g.scale = scale[i];
+        g.inv_scale = inv[i];
+        g.rscale = 1.0f / inv[i];
+        if (cfg->fixed_multi_scale_tile_size) {
+            g.tile_h = cfg->tile_h;
+            g.tile_w = cfg->tile_w;
+        } else {
+            g.tile_h = (int)((float)cfg->tile_h * inv[i]);
+            g.tile_w = (int)((float)cfg->tile_w * inv[i]);
+        }
+        // the reference divides by 128/tile_w (orb_FAST_apply_NMS_G.cu:1434); tile_h <= 256 is this library's key width
+        if (g.tile_w < 1 || g.tile_w > 128 || g.tile_h < 1 || g.tile_h > 256) {
+            delete h;
+            return fail(JSFE_ERR_INVALID, "level %d tile %dx%d unsupported (need 1<=tile_w<=128, 1<=tile_h<=256)", i, g.tile_h, g.tile_w);
+        }
+        g.n_tile_h = (g.h - 1) / g.tile_h + 1;
+        g.n_tile_w = (g.w - 1) / g.tile_w + 1;
+        g.cell_offset = cells;
+        cells += g.n_tile_h * g.n_tile_w;
+        g.tile_row_offset = tile_rows;
+        tile_rows += g.n_tile_h;
+        // y-lane count of the reference's launch (orb_FAST_apply_NMS_G.cu:1405-1431)
+        int n_loc = std::max(1, std::min(10, g.tile_w / 3));
+        n_loc = std::min(n_loc, g.tile_h);
+        int T = (g.tile_h - 1) / n_loc + 1;
+        if (T * 128 > 1024) T = 1024 / 128;
+        g.T = T;
+        g.cells_per_block = std::max(1, std::min(g.n_tile_w, 192 / g.tile_w));
+        g.blocks_per_row = (g.n_tile_w + g.cells_per_block - 1) / g.cells_per_block;
+        g.block_offset = items;
+        items += g.blocks_per_row * g.n_tile_h;
+        const size_t gw = (size_t)g.cells_per_block * g.tile_w;
+        const size_t pw = align_up(gw + 8 + 16, 16), pr = g.tile_h + 8;
+        const size_t sw = (gw + 3) & ~(size_t)1;
+        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 + 16);
+        g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
+        if (i >= 1) P.pyr_group_start[i + 1] = P.pyr_group_start[i] + g.h * (g.pitch / 4);
+    }
+    P.pyr_groups_total = P.L > 1 ? P.pyr_group_start[P.L] : 0;
+    P.fast_items_total = items;
+    P.cap = cells;
+    P.n_tile_rows = tile_rows;
+    h->fast_smem = smem_max;
+    if (cells >= 65535) { delete h; return fail(JSFE_ERR_INVALID, "more than 65534 NMS cells per image"); }
+
+    // ---- tables
+    jsfe::DevTables* T = new jsfe::DevTables;
+    memset(T, 0, sizeof *T);
+    for (int m = 0; m < 0xFFFF; ++m) {  // scan procedure of orb_gpu.cpp:366-436; entry 0xFFFF stays 0
+        int run = 0, accepted = 0;
+        for (int bit = 15; bit >= 0; --bit) {
+            if (m & (1 << bit)) ++run;
+            else {
+                if (run >= cfg->fast_n_min && run <= cfg->fast_n_max) { accepted = 1; break; }
+                run = 0;
+            }
+        }
+        if (!accepted)
+            for (int bit = 15; bit >= 0; --bit) { if (m & (1 << bit)) ++run; else break; }
+        if (run >= cfg->fast_n_min && run <= cfg->fast_n_max) T->lut_bits[m >> 5] |= 1u << (m & 31);
+    }
+    {  // umax (orb_gpu.cpp:161-182)
+        const int R = 15;
+        const double half = (double)((float)R * std::sqrt(2.f) / 2);
+        const int vmax = (int)std::floor(half + 1), vmin = (int)std::ceil(half);
+        for (int v = 0; v <= vmax; ++v) T->umax[v] = (int)std::lrint(std::sqrt((double)(R * R) - (double)(v * v)));
+        for (int v = R, v0 = 0; v >= vmin; --v) {
+            while (T->umax[v0] == T->umax[v0 + 1]) ++v0;
+            T->umax[v] = v0;
+            ++v0;
+        }
+    }
+    {  // 7x7 sigma=10 weights (orb_gpu.cpp:196-218): double exp of a float argument, float sum, float divide
+        const float sigma2 = 10.0f * 10.0f;
+        float sum = 0;
+        int n = 0;
+        for (int j = -3; j <= 3; ++j)
+            for (int k = -3; k <= 3; ++k) {
+                const float arg = (float)(-(j * j + k * k)) / (2 * sigma2);
+                T->gauss[n] = (float)std::exp((double)arg);
+                sum += T->gauss[n];
+                ++n;
+            }
+        for (int i = 0; i < 49; ++i) T->gauss[i] /= sum;
+    }
+    for (int i = 0; i < 512; ++i) {  // orb_bitpattern.cpp:266-273
+        T->pat_x[i] = (int8_t)kPattern[2 * i];
+        T->pat_y[i] = (int8_t)kPattern[2 * i + 1];
+    }
+    for (int i = 0; i < P.L; ++i) column_rank(P.lv[i].tile_w, T->col_rank[i], T->col_by_rank[i]);
+
+    int rc = JSFE_OK;
+    auto bail = [&](int code) { delete T; jsfe_destroy(h); return code; };
+    jsfe::DevTables* dT = nullptr;
+    if ((rc = dev_alloc(h, &dT, 1)) != JSFE_OK) return bail(rc);
+    if (cudaMemcpy(dT, T, sizeof *T, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(JSFE_ERR_CUDA, "table upload failed"));
+    P.tab = dT;
+    delete T;
+    T = nullptr;
+
+    // ---- images + masks
+    const size_t M = (size_t)h->max_images, cap = (size_t)P.cap;
+    for (int i = 0; i < P.L; ++i) {
+        jsfe::LevelGeom& g = P.lv[i];
+        if ((rc = dev_alloc(h, &g.img, g.slot_stride * M)) != JSFE_OK) return bail(rc);
+        g.mask = nullptr;
+        if (cfg->mask) {  // INTER_NEAREST + THRESH_BINARY(10), orb_gpu.cpp:78-90
+            std::vector<uint8_t> m((size_t)g.h * g.pitch, 0);
+            const double ifx = 1.0 / ((double)g.w / cfg->width), ify = 1.0 / ((double)g.h / cfg->height);
+            for (int y = 0; y < g.h; ++y) {
+                const int sy = std::min((int)std::floor(y * ify), cfg->height - 1);
+                for (int x = 0; x < g.w; ++x) {
+                    const int sx = std::min((int)std::floor(x * ifx), cfg->width - 1);
+                    m[(size_t)y * g.pitch + x] = cfg->mask[(size_t)sy * cfg->mask_pitch + sx] > 10 ? 255 : 0;
+                }
+            }
+            uint8_t* dm = nullptr;
+            if ((rc = dev_alloc(h, &dm, m.size())) != JSFE_OK) return bail(rc);
+            if (cudaMemcpy(dm, m.data(), m.size(), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(JSFE_ERR_CUDA, "mask upload failed"));
+            g.mask = dm;
+        }
+    }
+    // ---- per-slot arrays
+    if ((rc = dev_alloc(h, &P.cell_x, M * cap)) || (rc = dev_alloc(h, &P.cell_y, M * cap)) || (rc = dev_alloc(h, &P.cell_s, M * cap)) ||
+        (rc = dev_alloc(h, &P.kp_x, M * cap)) || (rc = dev_alloc(h, &P.kp_y, M * cap)) || (rc = dev_alloc(h, &P.kp_s, M * cap)) ||
+        (rc = dev_alloc(h, &P.kp_l, M * cap)) || (rc = dev_alloc(h, &P.kp_angle, M * cap)) || (rc = dev_alloc(h, &P.n_kp, M)) ||
+        (rc = dev_alloc(h, &P.n_per_level, M * JSFE_MAXL)) || (rc = dev_alloc(h, &P.row_start, M * (size_t)(tile_rows + 1))) ||
+        (rc = dev_alloc(h, &P.kps, M * 6 * cap)) || (rc = dev_alloc(h, &P.desc, M * cap * 32)) ||
+        (rc = dev_alloc(h, &P.u_right, M * cap)) || (rc = dev_alloc(h, &P.depth, M * cap)) ||
+        (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
+        (rc = dev_alloc(h, &P.sad_best, M * cap)))
+        return bail(rc);
+    // ---- pinned staging
+    if (cudaMallocHost((void**)&h->h_n, M * sizeof(int32_t)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_kps, M * 6 * cap * sizeof(int32_t) + 16) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_desc, M * cap * 32 + 16) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_ur, M * cap * sizeof(float) + 16) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_dp, M * cap * sizeof(float) + 16) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_misc, 5 * cap * sizeof(int32_t) + 16) != cudaSuccess)
+        return bail(fail(JSFE_ERR_CUDA, "pinned host allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (h->fast_smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(jsfe::k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
+            return bail(fail(JSFE_ERR_CUDA, "k_fast_cells needs %zu bytes of shared memory", h->fast_smem));
+    }
+    CU(cudaDeviceSynchronize());
+    *out = h;
+    return JSFE_OK;
+}
+
+int jsfe_destroy(jsfe_handle* h) {
+    if (!h) return JSFE_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->dev_allocs) cudaFree(p);
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    if (h->h_n) cudaFreeHost(h->h_n);
+    if (h->h_kps) cudaFreeHost(h->h_kps);
+    if (h->h_desc) cudaFreeHost(h->h_desc);
+    if (h->h_ur) cudaFreeHost(h->h_ur);
+    if (h->h_dp) cudaFreeHost(h->h_dp);
+    if (h->h_misc) cudaFreeHost(h->h_misc);
+    delete h;
+    return JSFE_OK;
+}
+
+int jsfe_max_keypoints(const jsfe_handle* h) { return h ? h->P.cap : fail(JSFE_ERR_INVALID, "null handle"); }
+int jsfe_num_levels(const jsfe_handle* h) { return h ? h->P.L : fail(JSFE_ERR_INVALID, "null handle"); }
+int64_t jsfe_launch_count(const jsfe_handle* h) { return h ? h->launches : 0; }
+
+int jsfe_get_level_info(const jsfe_handle* h, int level, jsfe_level_info* out) {
+    if (!h || !out || level < 0 || level >= h->P.L) return fail(JSFE_ERR_INVALID, "bad level");
+    const jsfe::LevelGeom& g = h->P.lv[level];
+    out->height = g.h; out->width = g.w; out->pitch = g.pitch;
+    out->tile_h = g.tile_h; out->tile_w = g.tile_w; out->n_tile_h = g.n_tile_h; out->n_tile_w = g.n_tile_w;
+    out->cell_offset = g.cell_offset; out->scale = g.scale; out->inv_scale = g.inv_scale;
+    return JSFE_OK;
+}
+
+int jsfe_set_images(jsfe_handle* h, int first_slot, int n, const uint8_t* src, int64_t row_pitch, int64_t image_stride,
+                    int src_is_device, void* stream) {
+    int rc = check_slots(h, first_slot, n);
+    if (rc) return rc;
+    if (!src || row_pitch < h->P.W0) return fail(JSFE_ERR_INVALID, "bad source image pointer / pitch");
+    CU(cudaSetDevice(h->device));
+    const jsfe::LevelGeom& g = h->P.lv[0];
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (image_stride == row_pitch * (int64_t)g.h && g.slot_stride == (size_t)g.pitch * g.h) {
+        // rows of consecutive images are equally spaced on both sides: one 2-D copy for the whole batch
+        CU(cudaMemcpy2DAsync(g.img + (size_t)first_slot * g.slot_stride, g.pitch, src, (size_t)row_pitch, g.w, (size_t)g.h * n, kind,
+                             (cudaStream_t)stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CU(cudaMemcpy2DAsync(g.img + (size_t)(first_slot + i) * g.slot_stride, g.pitch, src + (size_t)i * image_stride,
+                                 (size_t)row_pitch, g.w, g.h, kind, (cudaStream_t)stream));
+    }
+    return JSFE_OK;
+}
+
+int jsfe_slot_image(jsfe_handle* h, int slot, uint8_t** dev_ptr, int64_t* pitch) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (dev_ptr) *dev_ptr = h->P.lv[0].img + (size_t)slot * h->P.lv[0].slot_stride;
+    if (pitch) *pitch = h->P.lv[0].pitch;
+    return JSFE_OK;
+}
+
+int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
+    int rc = check_slots(h, first_slot, n);
+    if (rc) return rc;
+    if (n == 0) return JSFE_OK;
+    if (h->cfg.apply_nms_ms && h->P.L > 1) return fail(JSFE_ERR_INVALID, "cross-scale NMS (apply_nms_ms) is not implemented yet");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const jsfe::Params& P = h->P;
+    if (P.pyr_groups_total > 0) {
+        StageTimer t(h, st, 0);
+        jsfe::k_pyramid<<<dim3((P.pyr_groups_total + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+        if ((rc = post_launch(h, "k_pyramid"))) return rc;
+    }
+    {
+        StageTimer t(h, st, 1);
+        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
+    }
+    if ((rc = post_launch(h, "k_fast_cells"))) return rc;
+    {
+        StageTimer t(h, st, 2);
+        jsfe::k_compact<<<n, 1024, 0, st>>>(P, first_slot);
+    }
+    if ((rc = post_launch(h, "k_compact"))) return rc;
+    {
+        StageTimer t(h, st, 3);
+        jsfe::k_orient_desc<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, first_slot);
+    }
+    if ((rc = post_launch(h, "k_orient_desc"))) return rc;
+    return JSFE_OK;
+}
+
+int jsfe_stereo_match(jsfe_handle* h, int first_pair, int n, int th_high, int th_low, float mb, float mbf, void* stream) {
+    int rc = check_slots(h, 2 * first_pair, 2 * n);
+    if (rc) return rc;
+    if (n == 0) return JSFE_OK;
+    if (!(mb > 0.0f) || th_high < 0 || th_high > 32767) return fail(JSFE_ERR_INVALID, "bad stereo parameters");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const jsfe::Params& P = h->P;
+    {
+        StageTimer t(h, st, 4);
+        jsfe::k_stereo_match<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, first_pair, th_high, th_low, mb, mbf);
+    }
+    if ((rc = post_launch(h, "k_stereo_match"))) return rc;
+    StageTimer t(h, st, 5);
+    jsfe::k_stereo_outlier<<<n, 1024, 0, st>>>(P, first_pair);
+    if ((rc = post_launch(h, "k_stereo_outlier"))) return rc;
+    return JSFE_OK;
+}
+
+int jsfe_slot_view_get(const jsfe_handle* h, int slot, jsfe_slot_view* out) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (!out) return fail(JSFE_ERR_INVALID, "null out");
+    const jsfe::Params& P = h->P;
+    const size_t cap = P.cap, s = slot;
+    out->n_keypoints = P.n_kp + s;
+    out->n_per_level = P.n_per_level + s * JSFE_MAXL;
+    out->kps = P.kps + s * 6 * cap;
+    out->desc = P.desc + s * cap * 32;
+    out->u_right = P.u_right + s * cap;
+    out->depth = P.depth + s * cap;
+    out->best_idx_r = P.best_idx + s * cap;
+    out->best_dist = P.best_dist + s * cap;
+    out->capacity = P.cap;
+    return JSFE_OK;
+}
+
+int jsfe_level_image(const jsfe_handle* h, int slot, int level, const uint8_t** dev_ptr, int32_t* height, int32_t* width, int64_t* pitch) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (level < 0 || level >= h->P.L) return fail(JSFE_ERR_INVALID, "bad level");
+    const jsfe::LevelGeom& g = h->P.lv[level];
+    if (dev_ptr) *dev_ptr = g.img + (size_t)slot * g.slot_stride;
+    if (height) *height = g.h;
+    if (width) *width = g.w;
+    if (pitch) *pitch = g.pitch;
+    return JSFE_OK;
+}
+
+int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out, void* stream) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int n = h->h_n[0];
+    if (n_out) *n_out = n;
+    if (n > 0 && (dst_kps_dev || dst_desc_dev)) {
+        jsfe::k_pack<<<(8 * n + 255) / 256, 256, 0, st>>>(h->P, slot, n, dst_kps_dev, dst_desc_dev);
+        if ((rc = post_launch(h, "k_pack"))) return rc;
+    }
+    return JSFE_OK;
+}
+
+int jsfe_get_keypoints(jsfe_handle* h, int slot, int32_t* kps_host, uint8_t* desc_host, int32_t* n_out, void* stream) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap = h->P.cap;
+    CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_kps, h->P.kps + (size_t)slot * 6 * cap, 6 * cap * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_desc, h->P.desc + (size_t)slot * cap * 32, cap * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int n = h->h_n[0];
+    if (n_out) *n_out = n;
+    if (kps_host)
+        for (int pl = 0; pl < 6; ++pl) memcpy(kps_host + (size_t)pl * n, h->h_kps + (size_t)pl * cap, (size_t)n * sizeof(int32_t));
+    if (desc_host) memcpy(desc_host, h->h_desc, (size_t)n * 32);
+    return JSFE_OK;
+}
+
+int jsfe_get_stereo(jsfe_handle* h, int pair, float* u_right_host, float* depth_host, int32_t* best_idx_r_host,
+                    int32_t* best_dist_host, int32_t* n_left_out, void* stream) {
+    int rc = check_slots(h, 2 * pair, 2);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap = h->P.cap, s = (size_t)2 * pair;
+    CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_misc, h->P.u_right + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_misc + cap, h->P.depth + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_misc + 2 * cap, h->P.best_idx + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_misc + 3 * cap, h->P.best_dist + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int n = h->h_n[0];
+    if (n_left_out) *n_left_out = n;
+    if (u_right_host) memcpy(u_right_host, h->h_misc, (size_t)n * 4);
+    if (depth_host) memcpy(depth_host, h->h_misc + cap, (size_t)n * 4);
+    if (best_idx_r_host) memcpy(best_idx_r_host, h->h_misc + 2 * cap, (size_t)n * 4);
+    if (best_dist_host) memcpy(best_dist_host, h->h_misc + 3 * cap, (size_t)n * 4);
+    return JSFE_OK;
+}
+
+int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_results* out, void* stream) {
+    int rc = check_slots(h, first_slot, n);
+    if (rc) return rc;
+    if (!out) return fail(JSFE_ERR_INVALID, "null out");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap = h->P.cap, f = first_slot, N = n;
+    CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + f, N * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_kps, h->P.kps + f * 6 * cap, N * 6 * cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_desc, h->P.desc + f * cap * 32, N * cap * 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_ur, h->P.u_right + f * cap, N * cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->h_dp, h->P.depth + f * cap, N * cap * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out->n_keypoints = h->h_n;
+    out->kps = h->h_kps;
+    out->desc = h->h_desc;
+    out->u_right = h->h_ur;
+    out->depth = h->h_dp;
+    out->capacity = h->P.cap;
+    out->bytes = (int64_t)(N * 4 + N * 6 * cap * 4 + N * cap * 32 + 2 * N * cap * 4);
+    return JSFE_OK;
+}
+
+int jsfe_profile_enable(jsfe_handle* h, int on) {
+    if (!h) return fail(JSFE_ERR_INVALID, "null handle");
+    h->profiling = on != 0;
+    return JSFE_OK;
+}
+
+int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, int n_stages) {
+    if (!h || !stage_ms || !stage_launches || n_stages < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(h->device));
+    for (int i = 0; i < n_stages; ++i) { stage_ms[i] = 0.f; stage_launches[i] = 0; }
+    for (auto& sp : h->spans) {
+        CU(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (sp.stage < n_stages) { stage_ms[sp.stage] += ms; ++stage_launches[sp.stage]; }
+        h->event_pool.push_back(sp.a);
+        h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+    return JSFE_OK;
+}
+
+int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (level < 0 || level >= h->P.L || !host_dst) return fail(JSFE_ERR_INVALID, "bad level / dst");
+    CU(cudaSetDevice(h->device));
+    const jsfe::LevelGeom& g = h->P.lv[level];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy2D(host_dst, g.w, g.img + (size_t)slot * g.slot_stride, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    return JSFE_OK;
+}
+
+int jsfe_debug_cells(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    const size_t cap = h->P.cap, o = (size_t)slot * cap;
+    if (x) CU(cudaMemcpy(x, h->P.cell_x + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (y) CU(cudaMemcpy(y, h->P.cell_y + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (score) CU(cudaMemcpy(score, h->P.cell_s + o, cap * 4, cudaMemcpyDeviceToHost));
+    return JSFE_OK;
+}
+
+int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score, int32_t* level, float* angle_rad) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    const size_t cap = h->P.cap, o = (size_t)slot * cap;
+    if (x) CU(cudaMemcpy(x, h->P.kp_x + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (y) CU(cudaMemcpy(y, h->P.kp_y + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (score) CU(cudaMemcpy(score, h->P.kp_s + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (level) CU(cudaMemcpy(level, h->P.kp_l + o, cap * 4, cudaMemcpyDeviceToHost));
+    if (angle_rad) CU(cudaMemcpy(angle_rad, h->P.kp_angle + o, cap * 4, cudaMemcpyDeviceToHost));
+    return JSFE_OK;
+}
+
+}  // extern "C"

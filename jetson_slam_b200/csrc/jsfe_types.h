@@ -1,0 +1,68 @@
+// jsfe_types.h -- plain structs shared by the host side and the kernels of libjsfe.so.
+#ifndef JSFE_TYPES_H
+#define JSFE_TYPES_H
+
+#include <stdint.h>
+
+#define JSFE_MAXL 16
+#define JSFE_B 20               // BORDER_SKIP (reference include/cuda/orb_gpu.hpp:17)
+#define JSFE_PATCH_R 21         // 18 (max rotated rBRIEF offset) + 3 (blur radius)
+#define JSFE_PATCH_ROWS 43      // 2*21+1
+#define JSFE_PATCH_PITCH 48     // bytes per staged patch row (12 aligned words)
+
+namespace jsfe {
+
+// Per-level geometry + device pointers (slot 0; slot s = base + s * slot_stride).
+struct LevelGeom {
+    int h, w, pitch;                 // pitch: bytes per row, multiple of 16; bytes [w, pitch) are zero
+    int tile_h, tile_w, n_tile_h, n_tile_w;
+    int cell_offset;                 // level_offset_[l] in the reference
+    int tile_row_offset;             // running sum of n_tile_h (index into row_start)
+    int T;                           // y-lanes of the reference's NMS launch (tie-break rule)
+    int cells_per_block;             // NMS cells one k_fast_cells block owns (adjacent in a tile row)
+    int blocks_per_row;              // ceil(n_tile_w / cells_per_block)
+    int block_offset;                // first k_fast_cells work item of this level
+    float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
+    unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
+    uint8_t* img;                    // level image of slot 0
+    const uint8_t* mask;             // [h][pitch] or nullptr (all pass); shared by all slots
+};
+
+// Small read-only tables in global memory (one copy per handle).
+struct DevTables {
+    uint32_t lut_bits[2048];   // FAST arc LUT, 1 bit per 16-bit ring mask; bit 0xFFFF = 0
+    int umax[16];              // radius-15 disc half-widths
+    float gauss[49];           // 7x7 sigma=10 weights, row-major
+    int8_t pat_x[512], pat_y[512];
+    uint8_t col_rank[JSFE_MAXL][128];     // column priority of the reference's smem tree (0 wins ties)
+    uint8_t col_by_rank[JSFE_MAXL][128];  // inverse permutation
+};
+
+struct Params {
+    int L;
+    int cap;        // max keypoints per slot (= number of NMS cells over all levels)
+    int n_tile_rows;  // sum of n_tile_h
+    int threshold;  // th_FAST_MAX
+    int H0, W0;
+    int pyr_groups_total;             // 4-pixel groups over levels 1..L-1
+    int pyr_group_start[JSFE_MAXL + 1];
+    int fast_items_total;             // k_fast_cells work items over all levels
+    LevelGeom lv[JSFE_MAXL];
+    const DevTables* tab;
+    // per-slot arrays, slot stride = cap unless noted
+    int *cell_x, *cell_y, *cell_s;                    // per NMS cell candidates
+    int *kp_x, *kp_y, *kp_s, *kp_l;                   // compacted, level coordinates, final order
+    float* kp_angle;                                  // radians
+    int* n_kp;                                        // [slot]
+    int* n_per_level;                                 // [slot][JSFE_MAXL]
+    int* row_start;                                   // [slot][n_tile_rows + 1] first keypoint index of each (level, tile row)
+    int* kps;                                         // [slot][6][cap] output planes
+    uint8_t* desc;                                    // [slot][cap][32]
+    float *u_right, *depth;                           // [slot][cap]
+    int *best_idx, *best_dist;                        // [slot][cap]
+    int* sad_best;                                    // [slot][cap]: accepted SAD minimum or -1
+};
+
+}  // namespace jsfe
+
+#endif

@@ -1,0 +1,291 @@
+"""Host-side binding of libjsfe.so (ctypes over the C ABI in include/jsfe.h).
+
+`Frontend` is the batched B200 entry point (one handle = many image slots on one GPU);
+`ORBExtractor` / `compute_stereo_matches` mirror the reference's per-frame interface
+(Jetson_SLAM::ORBExtractor, include/ORBextractor.h:21-42; ORB_GPU::ORB_compute_stereo_match,
+include/cuda/orb_gpu.hpp:218-229) with the same argument meaning and output layout, so parity
+tests read like calls into the reference.
+
+There is NO fallback: if libjsfe.so is missing or no CUDA device is present this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjsfe.so")
+
+
+class JsfeError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("height", C.c_int32), ("width", C.c_int32), ("n_levels", C.c_int32), ("scale_factor", C.c_float),
+        ("fast_n_min", C.c_int32), ("fast_n_max", C.c_int32), ("th_fast_min", C.c_int32), ("th_fast_max", C.c_int32),
+        ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("fixed_multi_scale_tile_size", C.c_int32),
+        ("apply_nms_ms", C.c_int32), ("nms_ms_mode_gpu", C.c_int32),
+        ("mask", C.c_void_p), ("mask_pitch", C.c_int64), ("device_id", C.c_int32), ("max_images", C.c_int32),
+    ]
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("pitch", C.c_int32), ("tile_h", C.c_int32),
+                ("tile_w", C.c_int32), ("n_tile_h", C.c_int32), ("n_tile_w", C.c_int32), ("cell_offset", C.c_int32),
+                ("scale", C.c_float), ("inv_scale", C.c_float)]
+
+
+class SlotView(C.Structure):
+    _fields_ = [("n_keypoints", C.c_void_p), ("n_per_level", C.c_void_p), ("kps", C.c_void_p), ("desc", C.c_void_p),
+                ("u_right", C.c_void_p), ("depth", C.c_void_p), ("best_idx_r", C.c_void_p), ("best_dist", C.c_void_p),
+                ("capacity", C.c_int32)]
+
+
+class HostResults(C.Structure):
+    _fields_ = [("n_keypoints", C.POINTER(C.c_int32)), ("kps", C.POINTER(C.c_int32)), ("desc", C.POINTER(C.c_uint8)),
+                ("u_right", C.POINTER(C.c_float)), ("depth", C.POINTER(C.c_float)), ("capacity", C.c_int32),
+                ("bytes", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libjsfe.so (raises if it has not been built: `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JsfeError(f"{LIB_PATH} not built; run __graft_entry__.build(). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.jsfe_last_error.restype = C.c_char_p
+        L.jsfe_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+        L.jsfe_destroy.argtypes = [vp]
+        L.jsfe_max_keypoints.argtypes = [vp]
+        L.jsfe_num_levels.argtypes = [vp]
+        L.jsfe_get_level_info.argtypes = [vp, C.c_int, C.POINTER(LevelInfo)]
+        L.jsfe_set_images.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, C.c_int64, C.c_int, vp]
+        L.jsfe_slot_image.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
+        L.jsfe_extract.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.jsfe_stereo_match.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]
+        L.jsfe_slot_view_get.argtypes = [vp, C.c_int, C.POINTER(SlotView)]
+        L.jsfe_level_image.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int64)]
+        L.jsfe_pack_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
+        L.jsfe_get_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
+        L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
+        L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
+        L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
+        L.jsfe_debug_level_keypoints.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+        L.jsfe_profile_enable.argtypes = [vp, C.c_int]
+        L.jsfe_profile_read.argtypes = [vp, vp, vp, C.c_int]
+        L.jsfe_launch_count.restype = C.c_int64
+        L.jsfe_launch_count.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise JsfeError(f"jsfe error {rc}: {lib().jsfe_last_error().decode()}")
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class Frontend:
+    """One GPU, `max_images` image slots.  Pair p = slots (2p, 2p+1)."""
+
+    def __init__(self, height, width, n_levels=8, scale_factor=1.2, fast_n_min=9, fast_n_max=14, th_fast_min=7,
+                 th_fast_max=20, tile_h=30, tile_w=30, fixed_multi_scale_tile_size=0, apply_nms_ms=0,
+                 nms_ms_mode_gpu=1, mask=None, device=0, max_images=2):
+        self._h = None
+        self._mask = None
+        cfg = _Config(height, width, n_levels, scale_factor, fast_n_min, fast_n_max, th_fast_min, th_fast_max,
+                      tile_h, tile_w, int(fixed_multi_scale_tile_size), int(apply_nms_ms), int(nms_ms_mode_gpu),
+                      None, 0, device, max_images)
+        if mask is not None:
+            self._mask = np.ascontiguousarray(mask, np.uint8)
+            if self._mask.shape != (height, width):
+                raise ValueError("mask must be height x width")
+            cfg.mask = self._mask.ctypes.data
+            cfg.mask_pitch = width
+        h = C.c_void_p()
+        _check(lib().jsfe_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.height, self.width, self.n_levels, self.max_images = height, width, n_levels, max_images
+        self.device = device
+        self.max_kp = lib().jsfe_max_keypoints(self._h)
+        self.levels = []
+        for l in range(n_levels):
+            li = LevelInfo()
+            _check(lib().jsfe_get_level_info(self._h, l, C.byref(li)))
+            self.levels.append(li)
+        self.scale = np.array([li.scale for li in self.levels], np.float32)
+        self.inv_scale = np.array([li.inv_scale for li in self.levels], np.float32)
+
+    def close(self):
+        if self._h is not None:
+            lib().jsfe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- input
+    def set_images(self, images, first_slot=0, stream=None):
+        """images: u8 array [n, H, W] (or [H, W]) in host memory (pinned memory makes the copy asynchronous)."""
+        a = np.asarray(images)
+        if a.ndim == 2:
+            a = a[None]
+        if a.dtype != np.uint8 or a.shape[1:] != (self.height, self.width) or not a.flags.c_contiguous:
+            raise ValueError("images must be C-contiguous uint8 [n, H, W]")
+        _check(lib().jsfe_set_images(self._h, first_slot, a.shape[0], a.ctypes.data, self.width,
+                                     self.width * self.height, 0, _stream_ptr(stream)))
+
+    def set_images_ptr(self, ptr, n, row_pitch, image_stride, on_device, first_slot=0, stream=None):
+        _check(lib().jsfe_set_images(self._h, first_slot, n, C.c_void_p(int(ptr)), row_pitch, image_stride,
+                                     int(bool(on_device)), _stream_ptr(stream)))
+
+    def slot_image(self, slot):
+        p, pitch = C.c_void_p(), C.c_int64()
+        _check(lib().jsfe_slot_image(self._h, slot, C.byref(p), C.byref(pitch)))
+        return p.value, pitch.value
+
+    # ---- compute (asynchronous on `stream`)
+    def extract(self, first_slot=0, n=None, stream=None):
+        n = self.max_images - first_slot if n is None else n
+        _check(lib().jsfe_extract(self._h, first_slot, n, _stream_ptr(stream)))
+
+    def stereo_match(self, mb, mbf, first_pair=0, n=None, th_high=100, th_low=50, stream=None):
+        n = self.max_images // 2 - first_pair if n is None else n
+        _check(lib().jsfe_stereo_match(self._h, first_pair, n, th_high, th_low, mb, mbf, _stream_ptr(stream)))
+
+    # ---- results (synchronise)
+    def get_keypoints(self, slot, stream=None):
+        """-> (kps int32 [6, N] = x|y|score|angle_deg(f32 bits)|octave|size, desc u8 [N, 32]) in the reference layout."""
+        kps = np.zeros(6 * self.max_kp, np.int32)
+        desc = np.zeros(32 * self.max_kp, np.uint8)
+        n = C.c_int32()
+        _check(lib().jsfe_get_keypoints(self._h, slot, kps.ctypes.data, desc.ctypes.data, C.byref(n), _stream_ptr(stream)))
+        n = n.value
+        return kps[:6 * n].reshape(6, n).copy(), desc[:32 * n].reshape(n, 32).copy()
+
+    def get_stereo(self, pair, stream=None):
+        """-> (u_right f32[nL], depth f32[nL], best_idx_r i32[nL], best_dist i32[nL])."""
+        bufs = [np.zeros(self.max_kp, dt) for dt in (np.float32, np.float32, np.int32, np.int32)]
+        n = C.c_int32()
+        _check(lib().jsfe_get_stereo(self._h, pair, *[b.ctypes.data for b in bufs], C.byref(n), _stream_ptr(stream)))
+        return tuple(b[:n.value].copy() for b in bufs)
+
+    def download(self, first_slot=0, n=None, stream=None):
+        """Bulk D2H of n slots' result slabs into pinned staging; returns numpy views (valid until the next call)."""
+        n = self.max_images - first_slot if n is None else n
+        r = HostResults()
+        _check(lib().jsfe_download_results(self._h, first_slot, n, C.byref(r), _stream_ptr(stream)))
+        cap = r.capacity
+        as_np = np.ctypeslib.as_array
+        return {
+            "n": as_np(r.n_keypoints, (n,)), "kps": as_np(r.kps, (n, 6, cap)), "desc": as_np(r.desc, (n, cap, 32)),
+            "u_right": as_np(r.u_right, (n, cap)), "depth": as_np(r.depth, (n, cap)), "bytes": r.bytes,
+        }
+
+    def slot_view(self, slot):
+        v = SlotView()
+        _check(lib().jsfe_slot_view_get(self._h, slot, C.byref(v)))
+        return v
+
+    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms")
+
+    def profile(self, on=True):
+        _check(lib().jsfe_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """-> {kernel: (total_ms, launches)} since the last read (CUDA events on the launching stream)."""
+        ms = np.zeros(len(self.STAGES), np.float32)
+        cnt = np.zeros(len(self.STAGES), np.int64)
+        _check(lib().jsfe_profile_read(self._h, ms.ctypes.data, cnt.ctypes.data, len(self.STAGES)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.STAGES)}
+
+    def launch_count(self):
+        return int(lib().jsfe_launch_count(self._h))
+
+    # ---- stage inspection (tests)
+    def level_image(self, slot, level):
+        li = self.levels[level]
+        out = np.zeros((li.height, li.width), np.uint8)
+        _check(lib().jsfe_debug_level_image(self._h, slot, level, out.ctypes.data))
+        return out
+
+    def cells(self, slot):
+        x, y, s = (np.zeros(self.max_kp, np.int32) for _ in range(3))
+        _check(lib().jsfe_debug_cells(self._h, slot, x.ctypes.data, y.ctypes.data, s.ctypes.data))
+        return x, y, s
+
+    def level_keypoints(self, slot):
+        x, y, s, l = (np.zeros(self.max_kp, np.int32) for _ in range(4))
+        a = np.zeros(self.max_kp, np.float32)
+        _check(lib().jsfe_debug_level_keypoints(self._h, slot, x.ctypes.data, y.ctypes.data, s.ctypes.data,
+                                                l.ctypes.data, a.ctypes.data))
+        return x, y, s, l, a
+
+
+class ORBExtractor:
+    """Mirror of Jetson_SLAM::ORBExtractor (include/ORBextractor.h:21-98): same constructor argument order,
+    `extract(image)` returns the keypoint SoA and descriptors the reference leaves in its SyncedMem outputs."""
+
+    def __init__(self, im_height, im_width, scale_factor, n_levels, FAST_N_MIN, FAST_N_MAX, th_FAST_MIN, th_FAST_MAX,
+                 str_mask, tile_h, tile_w, fixed_multi_scale_tile_size, apply_nms_ms, nms_ms_mode_gpu, use_gpu=True,
+                 mask=None, device=0, _frontend=None, _slot=0):
+        if str_mask:
+            raise ValueError("mask files are not read here; pass the mask array via mask=")
+        self._fe = _frontend or Frontend(im_height, im_width, n_levels, scale_factor, FAST_N_MIN, FAST_N_MAX,
+                                         th_FAST_MIN, th_FAST_MAX, tile_h, tile_w, fixed_multi_scale_tile_size,
+                                         apply_nms_ms, nms_ms_mode_gpu, mask=mask, device=device, max_images=1)
+        self._slot = _slot
+        self.n_levels_ = n_levels
+        self.scale_factor_ = scale_factor
+
+    def extract(self, image):
+        self._fe.set_images(np.ascontiguousarray(image, np.uint8), first_slot=self._slot)
+        self._fe.extract(self._slot, 1)
+        return self._fe.get_keypoints(self._slot)
+
+    def get_levels(self): return self.n_levels_
+    def get_scale_factor(self): return self.scale_factor_
+    def get_scale_factors(self): return self._fe.scale.copy()
+    def get_inverse_scale_factors(self): return self._fe.inv_scale.copy()
+    def get_scale_sigma_squares(self): return (self._fe.scale * self._fe.scale).astype(np.float32)
+    def get_inverse_scale_sigma_squares(self): return (np.float32(1.0) / (self._fe.scale * self._fe.scale)).astype(np.float32)
+
+
+class StereoORB:
+    """Left/right extractor pair sharing one handle (slots 0/1) + the stereo matcher, i.e. what
+    Frame::Frame(imLeft, imRight, ...) does on the hot path (src/Frame.cpp:80-250)."""
+
+    def __init__(self, cfg, device=0):
+        self.cfg = cfg
+        self.fe = Frontend(**cfg.extractor_kwargs(), device=device, max_images=2)
+
+    def __call__(self, im_left, im_right, th_high=100, th_low=50):
+        self.fe.set_images(np.stack([im_left, im_right]).astype(np.uint8, copy=False))
+        self.fe.extract(0, 2)
+        self.fe.stereo_match(self.cfg.mb, self.cfg.mbf, 0, 1, th_high, th_low)
+        kl, dl = self.fe.get_keypoints(0)
+        kr, dr = self.fe.get_keypoints(1)
+        ur, dp, bi, bd = self.fe.get_stereo(0)
+        return {"kps_l": kl, "desc_l": dl, "kps_r": kr, "desc_r": dr, "u_right": ur, "depth": dp, "best_idx_r": bi,
+                "best_dist": bd}

@@ -1,0 +1,174 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI, against
+ (1) the CPU oracle on the same seeded inputs, stage by stage, and
+ (2) the committed golden vectors produced by the reference's own kernels (tests/golden/ref_*.npz).
+Bar: bit-exact for coordinates, scores, angles, descriptors, Hamming arg-min; u_right/depth are asserted
+bit-exact too (north_star allows 1e-4)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from jetson_slam_b200 import frontend, synth
+from jetson_slam_b200.configs import CONFIGS
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pair(cfg, L, R):
+    ol, orr = orc.Oracle(**cfg.extractor_kwargs()), orc.Oracle(**cfg.extractor_kwargs())
+    kl, dl = ol.extract(L)
+    kr, dr = orr.extract(R)
+    st = orc.stereo_match(ol, orr, kl, dl, kr, dr, cfg.mb, cfg.mbf)
+    return ol, orr, (kl, dl, kr, dr), st
+
+
+def _assert_pair_equal(out, kl, dl, kr, dr, st, tag=""):
+    ur, dp, bi, bd = st
+    assert out["kps_l"].shape == kl.shape, f"{tag} N_left {out['kps_l'].shape} vs {kl.shape}"
+    assert out["kps_r"].shape == kr.shape, f"{tag} N_right"
+    for r, nm in enumerate(("x", "y", "score", "angle", "octave", "size")):
+        assert np.array_equal(out["kps_l"][r], kl[r]), f"{tag} left {nm}"
+        assert np.array_equal(out["kps_r"][r], kr[r]), f"{tag} right {nm}"
+    assert np.array_equal(out["desc_l"], dl), f"{tag} left descriptors: {np.unpackbits(out['desc_l'] ^ dl).sum()} bits differ"
+    assert np.array_equal(out["desc_r"], dr), f"{tag} right descriptors"
+    if bi is not None:
+        assert np.array_equal(out["best_idx_r"], bi), f"{tag} Hamming arg-min"
+        assert np.array_equal(out["best_dist"], bd), f"{tag} Hamming distance"
+    assert np.array_equal(out["u_right"] >= 0, ur >= 0), f"{tag} match mask"
+    assert np.abs(out["u_right"] - ur).max(initial=0) <= 1e-4 and np.abs(out["depth"] - dp).max(initial=0) <= 1e-4 * max(1.0, np.abs(dp).max(initial=0))
+    assert np.array_equal(out["u_right"].view(np.int32), ur.view(np.int32)), f"{tag} u_right bits"
+    assert np.array_equal(out["depth"].view(np.int32), dp.view(np.int32)), f"{tag} depth bits"
+
+
+@pytest.mark.parametrize("name,seed", [("tiny", 0), ("tiny", 1), ("tiny-fixed", 0), ("C1", 0), ("C2", 0), ("C3", 0), ("C4", 0),
+                                       ("KITTI00-02", 0), ("EuRoC", 0), ("C5", 0)])
+def test_stages_match_oracle(name, seed):
+    cfg = CONFIGS[name]
+    L, R = synth.stereo_pair(cfg.height, cfg.width, seed)
+    ol, orr, (kl, dl, kr, dr), st = _oracle_pair(cfg, L, R)
+    s = frontend.StereoORB(cfg)
+    out = s(L, R)
+    fe = s.fe
+    for slot, o in ((0, ol), (1, orr)):
+        for l in range(cfg.n_levels):
+            assert np.array_equal(fe.level_image(slot, l), o.level_image(l)), f"pyramid level {l} slot {slot}"
+        cx, cy, cs = fe.cells(slot)
+        ox, oy, os_ = o.cells()
+        assert np.array_equal(cs, os_), f"cell scores slot {slot}: {np.count_nonzero(cs != os_)} differ"
+        pos = os_ > 0
+        assert np.array_equal(cx[pos], ox[pos]) and np.array_equal(cy[pos], oy[pos]), f"cell arg-max (tie-break) slot {slot}"
+        x, y, sc, lv, ang = fe.level_keypoints(slot)
+        n = o.n_keypoints()
+        idx = np.concatenate([o.level_offset[l] + np.arange(n[l]) for l in range(cfg.n_levels)]).astype(np.int64)
+        okx, oky, oks, oka = o.level_keypoints()
+        N = len(idx)
+        assert np.array_equal(x[:N], okx[idx]) and np.array_equal(y[:N], oky[idx]) and np.array_equal(sc[:N], oks[idx])
+        assert np.array_equal(ang[:N].view(np.int32), oka[idx].view(np.int32)), "orientation bits"
+    _assert_pair_equal(out, kl, dl, kr, dr, st, tag=name)
+    assert (st[0] >= 0).sum() > 0
+
+
+def _golden_cases():
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "ref_*_seed*.npz"))):
+        name, seed = os.path.basename(f)[4:-4].rsplit("_seed", 1)
+        out.append((name, int(seed)))
+    return out
+
+
+@pytest.mark.parametrize("name,seed", _golden_cases())
+def test_matches_reference_golden(name, seed):
+    """Same inputs as the reference run that produced the fixture -> identical outputs."""
+    cfg = CONFIGS[name]
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}_seed{seed}.npz"))
+    L, R = synth.stereo_pair(cfg.height, cfg.width, seed)
+    out = frontend.StereoORB(cfg)(L, R)
+    _assert_pair_equal(out, g["kps_l"], g["desc_l"], g["kps_r"], g["desc_r"], (g["u_right"], g["depth"], None, None), tag=name)
+
+
+def test_degenerate_inputs_match_reference_golden():
+    cfg = CONFIGS["C1"]
+    g = np.load(os.path.join(GOLDEN, "ref_degenerate_C1.npz"))
+    ex = frontend.ORBExtractor(cfg.height, cfg.width, cfg.scale_factor, cfg.n_levels, cfg.fast_n_min, cfg.fast_n_max,
+                               cfg.th_fast_min, cfg.th_fast_max, "", cfg.tile_h, cfg.tile_w, False, False, True)
+    for nm, img in synth.degenerate_images(cfg.height, cfg.width).items():
+        k, d = ex.extract(img)
+        assert k.shape == g[f"kps_{nm}"].shape and np.array_equal(k, g[f"kps_{nm}"]), nm
+        assert np.array_equal(d, g[f"desc_{nm}"]), nm
+
+
+def test_empty_pair_gives_no_matches():
+    cfg = CONFIGS["tiny"]
+    z = np.zeros((cfg.height, cfg.width), np.uint8)
+    out = frontend.StereoORB(cfg)(z, z)
+    assert out["kps_l"].shape == (6, 0) and out["u_right"].shape == (0,)
+
+
+def test_batch_slots_are_independent_and_order_invariant():
+    """8 pairs in one launch == the same pairs one at a time (slots do not interact)."""
+    cfg = CONFIGS["C1"]
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, s) for s in range(8)]
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=16)
+    fe.set_images(np.stack([im for p in pairs for im in p]))
+    fe.extract(0, 16)
+    fe.stereo_match(cfg.mb, cfg.mbf, 0, 8)
+    single = frontend.StereoORB(cfg)
+    for p, (L, R) in enumerate(pairs):
+        ref = single(L, R)
+        kl, dl = fe.get_keypoints(2 * p)
+        kr, dr = fe.get_keypoints(2 * p + 1)
+        ur, dp, bi, bd = fe.get_stereo(p)
+        assert np.array_equal(kl, ref["kps_l"]) and np.array_equal(kr, ref["kps_r"])
+        assert np.array_equal(dl, ref["desc_l"]) and np.array_equal(dr, ref["desc_r"])
+        assert np.array_equal(ur.view(np.int32), ref["u_right"].view(np.int32)) and np.array_equal(bi, ref["best_idx_r"])
+    d = fe.download(0, 16)
+    assert d["n"][0] == fe.get_keypoints(0)[0].shape[1] and d["bytes"] > 0
+
+
+def test_mask_matches_oracle():
+    cfg = CONFIGS["tiny"]
+    img, _ = synth.stereo_pair(cfg.height, cfg.width, 5)
+    mask = np.full((cfg.height, cfg.width), 255, np.uint8)
+    mask[:, : cfg.width // 2] = 0
+    mask[30:50, :] = 5
+    k0, d0 = orc.Oracle(**cfg.extractor_kwargs(), mask=mask).extract(img)
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), mask=mask, max_images=1)
+    fe.set_images(img)
+    fe.extract(0, 1)
+    k1, d1 = fe.get_keypoints(0)
+    assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE's full size (C2), 4 different pairs in one batch."""
+    cfg = CONFIGS["C2"]
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=8)
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, 10 + s) for s in range(4)]
+    fe.set_images(np.stack([im for p in pairs for im in p]))
+    fe.extract(0, 8)
+    fe.stereo_match(cfg.mb, cfg.mbf, 0, 4)
+    for p in range(4):
+        k, d = fe.get_keypoints(2 * p)
+        n = k.shape[1]
+        assert 0 < n <= fe.max_kp
+        assert (np.diff(k[4]) >= 0).all(), "keypoints are level-major"
+        ang = k[3].view(np.float32)
+        assert (ang > -180.0001).all() and (ang <= 180.0).all()
+        assert (k[2] > 0).all() and (k[2] <= 4080).all()
+        sc = fe.scale[k[4]]
+        assert (k[0] >= np.floor(20 * sc) - 1).all() and (k[0] < cfg.width).all()
+        ur, dp, bi, bd = fe.get_stereo(p)
+        m = ur >= 0
+        assert m.sum() > 50
+        disp = k[0][m].astype(np.float32) - ur[m]
+        assert (disp > 0).all() and (disp < cfg.mbf / cfg.mb).all()
+        assert np.allclose(dp[m], cfg.mbf / disp, rtol=1e-6)
+        assert (bd[m] < 75).all() and (bi[m] >= 0).all()
+        # idempotence: same slot again gives identical bytes
+    k_a, d_a = fe.get_keypoints(0)
+    fe.extract(0, 8)
+    k_b, d_b = fe.get_keypoints(0)
+    assert np.array_equal(k_a, k_b) and np.array_equal(d_a, d_b)
