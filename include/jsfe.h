@@ -156,6 +156,8 @@ int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_resul
 
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
+/* the 7x7-blurred level (descriptor input); zero outside [20,h-20)x[20,w-20) like the reference's image_gaussian_ */
+int jsfe_debug_level_blur(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
 int jsfe_debug_cells(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score /* capacity each */);
 int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y, int32_t* score, int32_t* level,
                                float* angle_rad /* capacity each, first N valid */);

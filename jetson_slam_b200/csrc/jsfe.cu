@@ -219,8 +219,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         items += g.blocks_per_row * g.n_tile_h;
         const size_t gw = (size_t)g.cells_per_block * g.tile_w;
         const size_t pw = align_up(gw + 8 + 16, 16), pr = g.tile_h + 8;
-        const size_t sw = (gw + 3) & ~(size_t)1;
-        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 + 16);
+        const size_t sw = (gw + 2 + 7) & ~(size_t)7;
+        smem_max = std::max(smem_max, pr * pw + 2 * (size_t)(g.tile_h + 2) * sw * 2 + 16);  // pixels + scores + work list
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
         if (i >= 1) P.pyr_group_start[i + 1] = P.pyr_group_start[i] + g.h * (g.pitch / 4);
     }
@@ -271,6 +271,35 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             }
         for (int i = 0; i < 49; ++i) T->gauss[i] /= sum;
     }
+    {  // separable factors of the 7x7 weights: w[j][k] = g[j]*g[k] in exact arithmetic, g = exp(-j^2/200)/sum
+        double g[7], gs = 0;
+        for (int j = 0; j < 7; ++j) { g[j] = std::exp(-(double)((j - 3) * (j - 3)) / 200.0); gs += g[j]; }
+        double worst = 0;
+        for (int j = 0; j < 7; ++j) { T->sep_a[j] = (float)(g[j] / gs); T->sep_b[j] = (float)(g[j] / gs); }
+        for (int j = 0; j < 7; ++j)
+            for (int k = 0; k < 7; ++k)
+                worst = std::max(worst, std::fabs((double)T->gauss[j * 7 + k] - (double)T->sep_a[j] * (double)T->sep_b[k]));
+        if (worst > 1e-8) { delete T; delete h; return fail(JSFE_ERR_INVALID, "separable blur factors off by %g", worst); }
+    }
+    {  // compass pre-test of k_fast_blur_cells: every accepted ring mask must contain `mode` adjacent compass bits
+        auto compass_ok = [](int m, int mode) {
+            const int c[4] = {(m >> 0) & 1, (m >> 4) & 1, (m >> 8) & 1, (m >> 12) & 1};
+            for (int s0 = 0; s0 < 4; ++s0) {
+                int all = 1;
+                for (int k = 0; k < mode; ++k) all &= c[(s0 + k) & 3];
+                if (all) return true;
+            }
+            return false;
+        };
+        int mode = std::min(3, std::max(0, cfg->fast_n_min / 4));
+        for (; mode > 0; --mode) {
+            bool ok = true;
+            for (int m = 0; m < 0xFFFF && ok; ++m)
+                if ((T->lut_bits[m >> 5] >> (m & 31)) & 1u) ok = compass_ok(m, mode);
+            if (ok) break;
+        }
+        P.compass_mode = mode;
+    }
     for (int i = 0; i < 512; ++i) {  // orb_bitpattern.cpp:266-273
         T->pat_x[i] = (int8_t)kPattern[2 * i];
         T->pat_y[i] = (int8_t)kPattern[2 * i + 1];
@@ -291,6 +320,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     for (int i = 0; i < P.L; ++i) {
         jsfe::LevelGeom& g = P.lv[i];
         if ((rc = dev_alloc(h, &g.img, g.slot_stride * M)) != JSFE_OK) return bail(rc);
+        if ((rc = dev_alloc(h, &g.blur, g.slot_stride * M)) != JSFE_OK) return bail(rc);  // stays 0 outside the blurred interior
         g.mask = nullptr;
         if (cfg->mask) {  // INTER_NEAREST + THRESH_BINARY(10), orb_gpu.cpp:78-90
             std::vector<uint8_t> m((size_t)g.h * g.pitch, 0);
@@ -318,6 +348,17 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
         (rc = dev_alloc(h, &P.sad_best, M * cap)))
         return bail(rc);
+    if (cfg->apply_nms_ms && P.L > 1) {
+        int ts = 64;
+        while (ts < 2 * P.cap) ts <<= 1;
+        P.ms_table_size = ts;
+        if ((rc = dev_alloc(h, &P.ms_keys, M * (size_t)ts)) || (rc = dev_alloc(h, &P.ms_sums, M * (size_t)ts)) ||
+            (rc = dev_alloc(h, &P.ms_cnts, M * (size_t)ts)) || (rc = dev_alloc(h, &P.ms_drop, M * cap)))
+            return bail(rc);
+        if ((size_t)P.cap * 4 > 48 * 1024 &&
+            cudaFuncSetAttribute(jsfe::k_nms_ms_buckets, cudaFuncAttributeMaxDynamicSharedMemorySize, P.cap * 4) != cudaSuccess)
+            return bail(fail(JSFE_ERR_CUDA, "k_nms_ms_buckets needs %d bytes of shared memory", P.cap * 4));
+    }
     // ---- pinned staging
     if (cudaMallocHost((void**)&h->h_n, M * sizeof(int32_t)) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_kps, M * 6 * cap * sizeof(int32_t) + 16) != cudaSuccess ||
@@ -327,7 +368,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         cudaMallocHost((void**)&h->h_misc, 5 * cap * sizeof(int32_t) + 16) != cudaSuccess)
         return bail(fail(JSFE_ERR_CUDA, "pinned host allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (h->fast_smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(jsfe::k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(jsfe::k_fast_blur_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
             return bail(fail(JSFE_ERR_CUDA, "k_fast_cells needs %zu bytes of shared memory", h->fast_smem));
     }
     CU(cudaDeviceSynchronize());
@@ -397,7 +438,6 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     int rc = check_slots(h, first_slot, n);
     if (rc) return rc;
     if (n == 0) return JSFE_OK;
-    if (h->cfg.apply_nms_ms && h->P.L > 1) return fail(JSFE_ERR_INVALID, "cross-scale NMS (apply_nms_ms) is not implemented yet");
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const jsfe::Params& P = h->P;
@@ -408,9 +448,17 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     }
     {
         StageTimer t(h, st, 1);
-        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
+        jsfe::k_fast_blur_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
     }
-    if ((rc = post_launch(h, "k_fast_cells"))) return rc;
+    if ((rc = post_launch(h, "k_fast_blur_cells"))) return rc;
+    if (h->cfg.apply_nms_ms && P.L > 1) {  // orb_gpu.cpp:665-712
+        {
+            StageTimer t(h, st, 6);
+            if (h->cfg.nms_ms_mode_gpu) jsfe::k_nms_ms_dense<<<n, 1024, 0, st>>>(P, first_slot);
+            else jsfe::k_nms_ms_buckets<<<n, 256, (size_t)P.cap * 4, st>>>(P, first_slot);
+        }
+        if ((rc = post_launch(h, "k_nms_ms"))) return rc;
+    }
     {
         StageTimer t(h, st, 2);
         jsfe::k_compact<<<n, 1024, 0, st>>>(P, first_slot);
@@ -582,6 +630,17 @@ int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_ds
     const jsfe::LevelGeom& g = h->P.lv[level];
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy2D(host_dst, g.w, g.img + (size_t)slot * g.slot_stride, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    return JSFE_OK;
+}
+
+int jsfe_debug_level_blur(jsfe_handle* h, int slot, int level, uint8_t* host_dst) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (level < 0 || level >= h->P.L || !host_dst) return fail(JSFE_ERR_INVALID, "bad level / dst");
+    CU(cudaSetDevice(h->device));
+    const jsfe::LevelGeom& g = h->P.lv[level];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy2D(host_dst, g.w, g.blur + (size_t)slot * g.slot_stride, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
     return JSFE_OK;
 }
 

@@ -59,11 +59,39 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 }
 
 // =================================================================================================
-// K2  k_fast_cells: FAST ring test + SAD score + fused 3x3 NMS + per-cell arg-max, one block per
-//     group of adjacent NMS cells.  The int32 score map of the reference never exists in HBM.
-//     replaces FASTComputeScoreGPU_patternSize_16_lookup_mask (src/cuda/orb_FAST_compute_score.cu:1412-1560)
-//          and Tile_unrolling_reduction_kernel_v2        (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397)
+// K2  k_fast_blur_cells: one block per group of adjacent NMS cells.  The block stages its pixel tile
+//     (+4 px halo) in shared memory once and produces, from that single read of the level image,
+//       (a) FAST ring test + SAD score for every pixel of the group (+1 px halo), kept in shared memory
+//           -- the reference's int32 score map never exists in HBM;
+//       (b) the fused 3x3 NMS and per-cell arg-max under the reference's tie-break order;
+//       (c) the 7x7 sigma=10 blur of the group's pixels (descriptor input).
+//     replaces FASTComputeScoreGPU_patternSize_16_lookup_mask (src/cuda/orb_FAST_compute_score.cu:1412-1560),
+//              Tile_unrolling_reduction_kernel_v2             (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397),
+//              imgaussian_GPU                                 (src/cuda/orb_gaussian.cu:21-138).
+//
+//  FAST is ALU-bound, not HBM-bound, so the work is cut before it is parallelised:
+//   phase A  4 pixels per thread, packed-byte SWAR: |p-v| with VABSDIFF4, per-byte compares in the byte
+//            MSBs.  Only the 4 compass ring points are looked at; a pixel survives iff the reference's two
+//            early-outs do not fire AND enough adjacent compass points are all brighter / all darker for ANY
+//            accepted arc to exist (a necessary condition derived from FAST_N_MIN and verified against the LUT
+//            at create time).  Survivors are appended to a shared-memory work list (warp-aggregated).
+//   phase B  the work list is processed densely (no divergence): full 16-point masks, LUT, SAD.
+//  Every rejected pixel has score 0 in the reference too, so the score tile is bit-identical.
+//
+//  Blur: the reference's value is trunc(chain of 49 sequential FFMA).  We evaluate the separable form
+//  (7+7 FFMA, row sums kept in registers in a 7-deep rotating window, 4 columns per thread) whose distance to
+//  the chain is bounded by 5.3e-4; when the separable value lies within 6e-4 of an
+//  integer the exact chain is evaluated from the staged tile instead.  The stored byte is therefore always
+//  the reference's.
 // =================================================================================================
+#define JSFE_BLUR_EPS 6.0e-4f
+
+// per-byte MSB = (a > b), unsigned bytes; other bits are garbage
+__device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b) {
+    const unsigned t = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
+    return (a & ~b) | (~(a ^ b) & t);
+}
+
 __device__ __forceinline__ int fast_score(const uint8_t* c, int pw, int t, const uint32_t* __restrict__ lut) {
     const int v = c[0], vt = v + t, v_t = v - t;
     const int p4 = c[3], p12 = c[-3];
@@ -88,8 +116,24 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int pw, int t, const
     return hit ? sad : 0;
 }
 
-__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, int slot0) {
+// the reference's blur value: 49 sequential FFMA in row-major tap order, truncated (orb_gaussian.cu:37-135)
+__device__ __forceinline__ unsigned blur_exact(const uint8_t* pc, int pw, const float* __restrict__ gw) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = -3; i <= 3; ++i) {
+#pragma unroll
+        for (int j = -3; j <= 3; ++j) acc = __fmaf_rn(gw[(i + 3) * 7 + (j + 3)], (float)(unsigned)pc[i * pw + j], acc);
+    }
+    return __float2uint_rz(acc) & 0xFFu;
+}
+
+__device__ __forceinline__ float byte_f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+
+__global__ void __launch_bounds__(256) k_fast_blur_cells(const __grid_constant__ Params p, int slot0) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ unsigned s_best[192];
+    __shared__ int s_ncand;
+    __shared__ float s_gw[49];
     int l = 0;
     while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l + 1].block_offset) ++l;
     const LevelGeom& lv = p.lv[l];
@@ -102,15 +146,18 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int gx0 = ((X0 - 4) >> 4) << 4, gy0 = y0 - 4;
     const int PR = lv.tile_h + 8;
     const int PW = ((X0 + GW + 4 - gx0) + 15) & ~15;
-    const int SW = (GW + 2 + 1) & ~1;  // score row length (u16 elements)
+    const int SW = (GW + 2 + 7) & ~7;   // score row length (u16), multiple of 8 -> rows are 16-byte aligned
+    const int SR = lv.tile_h + 2;
     uint8_t* pix = smem;
     uint16_t* sc = reinterpret_cast<uint16_t*>(smem + (size_t)PR * PW);
+    uint16_t* cand = sc + (size_t)SR * SW;
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
+    const int tid = threadIdx.x, lane = tid & 31;
 
-    // stage the pixel tile (16-byte vectors; out-of-image = 0)
+    // ---- stage the pixel tile (16-byte vectors; out-of-image = 0), clear scores
     {
         const int vpr = PW >> 4, nvec = PR * vpr;
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        for (int i = tid; i < nvec; i += 256) {
             const int row = i / vpr, v = i - row * vpr;
             const int gy = gy0 + row, gx = gx0 + (v << 4);
             uint4 val = make_uint4(0, 0, 0, 0);
@@ -118,66 +165,354 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * lv.pitch + gx));
             *reinterpret_cast<uint4*>(pix + (size_t)row * PW + (v << 4)) = val;
         }
+        uint4* z = reinterpret_cast<uint4*>(sc);
+        const int nz = (SR * SW) >> 3;
+        for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+        if (tid < 192) s_best[tid] = 0;
+        if (tid == 0) s_ncand = 0;
+        if (tid < 49) s_gw[tid] = p.tab->gauss[tid];
     }
     __syncthreads();
 
-    // scores on the cell group + 1 px halo
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const uint32_t* lut = p.tab->lut_bits;
-    for (int ry = warp; ry < lv.tile_h + 2; ry += nwarps) {
-        const int y = y0 - 1 + ry;
-        const bool yin = (y >= JSFE_B) && (y < lv.h - JSFE_B);
-        for (int rx = lane; rx < GW + 2; rx += 32) {
-            const int x = X0 - 1 + rx;
-            int s = 0;
-            if (yin && x >= JSFE_B && x < lv.w - JSFE_B) {
-                if (lv.mask == nullptr || lv.mask[(size_t)y * lv.pitch + x])
-                    s = fast_score(pix + (size_t)(y - gy0) * PW + (x - gx0), PW, p.threshold, lut);
+    // ---- phase A: compass pre-test, 4 pixels per thread
+    {
+        const int cs0 = X0 - 1 - gx0;               // smem column of score column 0
+        const int g0 = cs0 >> 2, ngx = ((cs0 + GW + 1) >> 2) - g0 + 1;
+        const int total = SR * ngx;
+        const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
+        const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
+        const unsigned nT = ~T4 & 0x7f7f7f7fu;
+        const int mode = p.compass_mode;
+        const int dq = 256 / ngx, dr = 256 - dq * ngx;
+        int ry = tid / ngx, g = tid - ry * ngx;
+        const int niter = (total + 255) >> 8;   // warp-uniform trip count: the list append below is warp-collective
+        for (int it = 0, i = tid; it < niter; ++it, i += 256) {
+            unsigned pass = 0;
+            int c = 0;
+            if (i < total) {
+                const int y = y0 - 1 + ry;
+                c = (g0 + g) << 2;
+                const int xb = gx0 + c;
+                if (y >= JSFE_B && y < lv.h - JSFE_B && xb + 3 >= xlo && xb <= xhi) {
+                    const uint8_t* rp = pix + (size_t)(ry + 3) * PW + c;
+                    const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
+                    const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
+                    const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
+                    const unsigned P0 = *reinterpret_cast<const unsigned*>(rp + 3 * PW);   // ring 0  (0,+3)
+                    const unsigned P8 = *reinterpret_cast<const unsigned*>(rp - 3 * PW);   // ring 8  (0,-3)
+                    const unsigned P4 = __byte_perm(W1, W2, 0x6543);                       // ring 4  (+3,0)
+                    const unsigned P12 = __byte_perm(W0, W1, 0x4321);                      // ring 12 (-3,0)
+                    const unsigned v = W1;
+                    unsigned d, df0, df4, df8, df12, gt0, gt4, gt8, gt12;
+                    d = __vabsdiffu4(P0, v);  df0 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt0 = msb_gt(P0, v);
+                    d = __vabsdiffu4(P4, v);  df4 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt4 = msb_gt(P4, v);
+                    d = __vabsdiffu4(P8, v);  df8 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt8 = msb_gt(P8, v);
+                    d = __vabsdiffu4(P12, v); df12 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT)); gt12 = msb_gt(P12, v);
+                    // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
+                    const unsigned rej = (~df4 & ~df12) | (~df0 & ~df8);
+                    const unsigned b0 = df0 & gt0, b4 = df4 & gt4, b8 = df8 & gt8, b12 = df12 & gt12;
+                    const unsigned k0 = df0 & ~gt0, k4 = df4 & ~gt4, k8 = df8 & ~gt8, k12 = df12 & ~gt12;
+                    unsigned cond;
+                    if (mode == 2) cond = (b0 & b4) | (b4 & b8) | (b8 & b12) | (b12 & b0) | (k0 & k4) | (k4 & k8) | (k8 & k12) | (k12 & k0);
+                    else if (mode == 3) cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
+                                               (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
+                    else if (mode == 1) cond = b0 | b4 | b8 | b12 | k0 | k4 | k8 | k12;
+                    else cond = 0xffffffffu;
+                    pass = cond & ~rej & 0x80808080u;
+                    // column validity (score region, interior) and image mask
+                    unsigned vm = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) vm |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
+                    if (lv.mask != nullptr) {
+                        const unsigned mw = __ldg(reinterpret_cast<const unsigned*>(lv.mask + (size_t)y * lv.pitch + xb));
+                        vm &= msb_gt(mw, 0u);
+                    }
+                    pass &= vm;
+                }
             }
-            sc[ry * SW + rx] = (uint16_t)s;
+            // append survivors to the work list (warp-aggregated)
+            const int cnt = __popc(pass);
+            int incl = cnt;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= s) incl += n;
+            }
+            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31 && wtot) base = atomicAdd(&s_ncand, wtot);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            if (cnt) {
+                int o = base + incl - cnt;
+                const int idx0 = ry * SW + (c - cs0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (pass & (0x80u << (8 * k))) cand[o++] = (uint16_t)(idx0 + k);
+            }
+            g += dr; ry += dq;
+            if (g >= ngx) { g -= ngx; ++ry; }
         }
     }
     __syncthreads();
 
-    // per-cell arg-max of NMS survivors under the reference's tie-break order:
-    // (score desc, column priority of the smem tree asc, y-lane (y-y0)%T asc, y asc) packed into one key.
-    const uint8_t* rank = p.tab->col_rank[l];
-    const uint8_t* by_rank = p.tab->col_by_rank[l];
-    const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
-    for (int c = warp; c < ncells; c += nwarps) {
-        const int x0c = X0 + c * lv.tile_w;
-        const int cw = min(lv.tile_w, lv.w - x0c);
-        unsigned best = 0;
-        for (int y = ymin; y < ymax; ++y) {
-            const uint16_t* row = sc + (y - (y0 - 1)) * SW + (x0c - (X0 - 1));
-            for (int j = lane; j < cw; j += 32) {
-                const int s = row[j];
-                if (s == 0) continue;
-                const uint16_t* up = row + j - SW;
-                const uint16_t* dn = row + j + SW;
-                const bool ok = s >= up[-1] && s >= up[0] && s >= up[1] && s >= row[j - 1] && s >= row[j + 1] &&
-                                s >= dn[-1] && s >= dn[0] && s >= dn[1];
-                if (ok) {
-                    const int dy = y - y0;
-                    const unsigned key = ((unsigned)s << 18) | ((127u - rank[j]) << 11) | ((7u - (unsigned)(dy % lv.T)) << 8) |
-                                         (255u - (unsigned)dy);
-                    best = max(best, key);
+    // ---- phase B: full ring evaluation of the survivors, dense
+    {
+        const int n = s_ncand;
+        const float inv_sw = 1.0f / (float)SW;
+        const uint32_t* lut = p.tab->lut_bits;
+        for (int i = tid; i < n; i += 256) {
+            const int idx = cand[i];
+            const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
+            const int rx = idx - ry * SW;
+            const int s = fast_score(pix + (size_t)(ry + 3) * PW + (X0 - 1 - gx0 + rx), PW, p.threshold, lut);
+            sc[idx] = (uint16_t)s;
+        }
+    }
+
+    // ---- blur of the pixels this block owns (independent of the scores)
+    {
+        const int xa = max(X0, JSFE_B), xb_ = min(X0 + GW, lv.w - JSFE_B);      // owned x range [xa, xb_)
+        const int ya = max(y0, JSFE_B), yb = min(y0 + lv.tile_h, lv.h - JSFE_B); // owned y range [ya, yb)
+        if (xa < xb_ && ya < yb) {
+            const int cg0 = (xa - gx0) >> 2, ncg = ((xb_ - 1 - gx0) >> 2) - cg0 + 1;
+            int nchunk = 256 / ncg;
+            if (nchunk < 1) nchunk = 1;
+            const int rows = yb - ya;
+            if (nchunk > rows) nchunk = rows;
+            const int rpc = (rows + nchunk - 1) / nchunk;
+            float a[7], b[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { a[k] = p.tab->sep_a[k]; b[k] = p.tab->sep_b[k]; }
+            uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
+            for (int w = tid; w < ncg * nchunk; w += 256) {
+                const int ck = w / ncg, cg = w - ck * ncg;
+                const int r0 = ya + ck * rpc, r1 = min(r0 + rpc, yb);   // output rows [r0, r1)
+                if (r0 >= r1) continue;
+                const int c = (cg0 + cg) << 2;                           // smem column of the 4 outputs
+                const int xg = gx0 + c;
+                const int nin = r1 - r0 + 6;                            // input rows r0-3 .. r1+2
+                const uint8_t* rp = pix + (size_t)(r0 - 3 - gy0) * PW + c;
+                float q[4][7];
+                for (int base = 0; base < nin; base += 7) {
+#pragma unroll
+                    for (int ph = 0; ph < 7; ++ph) {
+                        const int ir = base + ph;
+                        if (ir < nin) {
+                            const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
+                            const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
+                            const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
+                            float f[10];  // pixels c-3 .. c+6
+                            f[0] = byte_f(W0, 1); f[1] = byte_f(W0, 2); f[2] = byte_f(W0, 3);
+                            f[3] = byte_f(W1, 0); f[4] = byte_f(W1, 1); f[5] = byte_f(W1, 2); f[6] = byte_f(W1, 3);
+                            f[7] = byte_f(W2, 0); f[8] = byte_f(W2, 1); f[9] = byte_f(W2, 2);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                float r = 0.0f;
+#pragma unroll
+                                for (int j = 0; j < 7; ++j) r = __fmaf_rn(b[j], f[k + j], r);
+                                q[k][ph] = r;
+                            }
+                            if (ir >= 6) {
+                                const int y = r0 + ir - 6;
+                                unsigned out = 0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float A = 0.0f;
+#pragma unroll
+                                    for (int j = 0; j < 7; ++j) A = __fmaf_rn(a[j], q[k][(ph + 1 + j) % 7], A);
+                                    const float fl = floorf(A);
+                                    const float fr = A - fl;
+                                    unsigned v = (unsigned)fl;
+                                    if (fr < JSFE_BLUR_EPS || fr > 1.0f - JSFE_BLUR_EPS)
+                                        v = blur_exact(pix + (size_t)(y - gy0) * PW + c + k, PW, s_gw);
+                                    out |= (v & 0xFFu) << (8 * k);
+                                }
+                                uint8_t* o = dst + (size_t)y * lv.pitch + xg;
+                                if (xg >= xa && xg + 3 < xb_) {
+                                    *reinterpret_cast<unsigned*>(o) = out;
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (xg + k >= xa && xg + k < xb_) o[k] = (uint8_t)(out >> (8 * k));
+                                }
+                            }
+                            rp += PW;
+                        }
+                    }
                 }
             }
         }
-        best = __reduce_max_sync(0xffffffffu, best);
-        if (lane == 0) {
-            int bx = x0c, by = y0, bs = 0;
-            if (best) {
-                bs = (int)(best >> 18);
-                bx = x0c + by_rank[127 - ((best >> 11) & 127u)];
-                by = y0 + 255 - (int)(best & 255u);
+    }
+    __syncthreads();
+
+    // ---- NMS + per-cell arg-max under the reference's tie-break order:
+    // (score desc, column priority of the smem tree asc, y-lane (y-y0)%T asc, y asc) packed into one key;
+    // all threads sweep the score tile, the few NMS survivors do one shared-memory atomicMax per cell.
+    {
+        const uint8_t* rank = p.tab->col_rank[l];
+        const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
+        const int nrow = ymax - ymin;
+        const int wv = min(GW, lv.w - X0);          // valid columns of the group
+        if (nrow > 0 && wv > 0) {
+            const int total = nrow * wv;
+            const int dq = 256 / wv, dr = 256 - dq * wv;
+            int yy = tid / wv, xx = tid - yy * wv;
+            for (int i = tid; i < total; i += 256) {
+                const int y = ymin + yy;
+                const uint16_t* row = sc + (y - (y0 - 1)) * SW + (xx + 1);
+                const int s = row[0];
+                if (s) {
+                    const uint16_t* up = row - SW;
+                    const uint16_t* dn = row + SW;
+                    const bool ok = s >= up[-1] && s >= up[0] && s >= up[1] && s >= row[-1] && s >= row[1] &&
+                                    s >= dn[-1] && s >= dn[0] && s >= dn[1];
+                    if (ok) {
+                        const int cell = xx / lv.tile_w, j = xx - cell * lv.tile_w;
+                        const int dy = y - y0;
+                        const unsigned key = ((unsigned)s << 18) | ((127u - rank[j]) << 11) | ((7u - (unsigned)(dy % lv.T)) << 8) |
+                                             (255u - (unsigned)dy);
+                        atomicMax(&s_best[cell], key);
+                    }
+                }
+                xx += dr; yy += dq;
+                if (xx >= wv) { xx -= wv; ++yy; }
             }
-            const size_t o = (size_t)slot * p.cap + lv.cell_offset + ty * lv.n_tile_w + tx0 + c;
-            p.cell_x[o] = bx;
-            p.cell_y[o] = by;
-            p.cell_s[o] = bs;
         }
+    }
+    __syncthreads();
+    if (tid < ncells) {
+        const uint8_t* by_rank = p.tab->col_by_rank[l];
+        const unsigned best = s_best[tid];
+        const int x0c = X0 + tid * lv.tile_w;
+        int bx = x0c, by = y0, bs = 0;
+        if (best) {
+            bs = (int)(best >> 18);
+            bx = x0c + by_rank[127 - ((best >> 11) & 127u)];
+            by = y0 + 255 - (int)(best & 255u);
+        }
+        const size_t o = (size_t)slot * p.cap + lv.cell_offset + ty * lv.n_tile_w + tx0 + tid;
+        p.cell_x[o] = bx;
+        p.cell_y[o] = by;
+        p.cell_s[o] = bs;
+    }
+}
+
+// =================================================================================================
+// K2b cross-scale NMS on the per-cell candidates (optional, apply_nms_ms && L > 1), one block per slot.
+//
+//  k_nms_ms_dense   -- the rule of the reference's GPU mode (src/cuda/orb_FAST_apply_NMS_MS.cu:18-467):
+//     every candidate is projected to its level-0 pixel (Y,X) = trunc(y*s), trunc(x*s); per pixel the
+//     scores over levels give sum and zeros = #levels without a candidate; a candidate survives iff
+//     sum*zeros at its pixel is >= sum*zeros at all 8 neighbouring pixels.  The reference materialises an
+//     L x H0 x W0 int32 volume (15 MB at KITTI size) and races on it; here the <= cap occupied pixels go
+//     into an open-addressing hash table in L2-resident scratch and all reads happen after all writes
+//     (the race-free two-phase semantics the oracle defines).
+//  k_nms_ms_buckets -- the rule of the reference's CPU mode (src/cuda/orb_FAST_apply_NMS_MS.cpp:15-122):
+//     candidates are bucketed by level-0 NMS tile of (trunc(x*s - 20), trunc(y*s - 20)); inside a bucket,
+//     in (level, cell) insertion order, every ordered pair of different levels within +-1 px zeroes the
+//     lower score (sequential, order-dependent -> one thread walks one bucket).
+// =================================================================================================
+__device__ __forceinline__ unsigned hash_px(int key) { return (unsigned)key * 2654435761u; }
+
+__global__ void __launch_bounds__(1024) k_nms_ms_dense(const __grid_constant__ Params p, int slot0) {
+    const int slot = slot0 + blockIdx.x;
+    const int ts = p.ms_table_size, mask = ts - 1;
+    int* keys = p.ms_keys + (size_t)slot * ts;
+    int* sums = p.ms_sums + (size_t)slot * ts;
+    int* cnts = p.ms_cnts + (size_t)slot * ts;
+    int* cs = p.cell_s + (size_t)slot * p.cap;
+    const int* cx = p.cell_x + (size_t)slot * p.cap;
+    const int* cy = p.cell_y + (size_t)slot * p.cap;
+    for (int i = threadIdx.x; i < ts; i += blockDim.x) { keys[i] = -1; sums[i] = 0; cnts[i] = 0; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.cap; c += blockDim.x) {
+        const int s = cs[c];
+        if (!s) continue;
+        int l = 0;
+        while (l + 1 < p.L && c >= p.lv[l + 1].cell_offset) ++l;
+        const int Y = __float2int_rz(__fmul_rn((float)cy[c], p.lv[l].scale));
+        const int X = __float2int_rz(__fmul_rn((float)cx[c], p.lv[l].scale));
+        const int key = Y * p.W0 + X;
+        unsigned h = hash_px(key) & mask;
+        for (;;) {
+            const int prev = atomicCAS(&keys[h], -1, key);
+            if (prev == -1 || prev == key) { atomicAdd(&sums[h], s); atomicAdd(&cnts[h], 1); break; }
+            h = (h + 1) & mask;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.cap; c += blockDim.x) {
+        const int s = cs[c];
+        if (!s) continue;
+        int l = 0;
+        while (l + 1 < p.L && c >= p.lv[l + 1].cell_offset) ++l;
+        const int Y = __float2int_rz(__fmul_rn((float)cy[c], p.lv[l].scale));
+        const int X = __float2int_rz(__fmul_rn((float)cx[c], p.lv[l].scale));
+        int prod[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int key = (Y + q / 3 - 1) * p.W0 + (X + q % 3 - 1);
+            unsigned h = hash_px(key) & mask;
+            int v = 0;
+            for (;;) {
+                const int k = keys[h];
+                if (k == key) { v = sums[h] * (p.L - cnts[h]); break; }
+                if (k == -1) break;
+                h = (h + 1) & mask;
+            }
+            prod[q] = v;
+        }
+        bool valid = true;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) valid &= prod[4] >= prod[q];
+        if (!valid) p.ms_drop[(size_t)slot * p.cap + c] = 1; else p.ms_drop[(size_t)slot * p.cap + c] = 0;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.cap; c += blockDim.x)
+        if (cs[c] && p.ms_drop[(size_t)slot * p.cap + c]) cs[c] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_nms_ms_buckets(const __grid_constant__ Params p, int slot0) {
+    extern __shared__ int s_bucket[];  // bucket id per cell (-1: no candidate)
+    const int slot = slot0 + blockIdx.x;
+    int* cs = p.cell_s + (size_t)slot * p.cap;
+    const int* cx = p.cell_x + (size_t)slot * p.cap;
+    const int* cy = p.cell_y + (size_t)slot * p.cap;
+    int* bx = p.ms_keys + (size_t)slot * p.ms_table_size;  // scratch: projected x / y per cell
+    int* by = p.ms_sums + (size_t)slot * p.ms_table_size;
+    const int nb = p.lv[0].n_tile_h * p.lv[0].n_tile_w;
+    for (int c = threadIdx.x; c < p.cap; c += blockDim.x) {
+        int b = -1;
+        if (cs[c] > 0) {
+            int l = 0;
+            while (l + 1 < p.L && c >= p.lv[l + 1].cell_offset) ++l;
+            const int x0 = __float2int_rz(__fsub_rn(__fmul_rn((float)cx[c], p.lv[l].scale), (float)JSFE_B));
+            const int y0 = __float2int_rz(__fsub_rn(__fmul_rn((float)cy[c], p.lv[l].scale), (float)JSFE_B));
+            bx[c] = x0;
+            by[c] = y0;
+            b = (y0 / p.lv[0].tile_h) * p.lv[0].n_tile_w + x0 / p.lv[0].tile_w;
+        }
+        s_bucket[c] = b;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        int ex[64], ey[64], es[64], el[64], ec[64];
+        int n = 0, l = 0;
+        for (int c = 0; c < p.cap; ++c) {
+            while (l + 1 < p.L && c >= p.lv[l + 1].cell_offset) ++l;
+            if (s_bucket[c] == b && n < 64) { ex[n] = bx[c]; ey[n] = by[c]; es[n] = cs[c]; el[n] = l; ec[n] = c; ++n; }
+        }
+        for (int j = 0; j < n; ++j)
+            for (int k = 0; k < n; ++k) {
+                if (j == k || el[j] == el[k]) continue;
+                if (es[j] && es[k]) {
+                    const int dx = ex[j] - ex[k], dy = ey[j] - ey[k];
+                    if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
+                        if (es[j] < es[k]) es[j] = 0; else es[k] = 0;
+                    }
+                }
+            }
+        for (int j = 0; j < n; ++j) cs[ec[j]] = es[j];
     }
 }
 
@@ -251,76 +586,71 @@ __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params
 }
 
 // =================================================================================================
-// K4  k_orient_desc: one warp per keypoint.  Stages the 43x43 level-image patch in shared memory,
-//     computes the intensity-centroid angle, evaluates the 7x7 blur ONLY at the 512 rotated sample
-//     points (same 49-FFMA chain, so bit-identical to blurring the whole level), forms the 256-bit
-//     descriptor and writes the final output planes.
-//     replaces FASTComputeOrientationGPU (src/cuda/orb_FAST_orientation.cu:17-65), imgaussian_GPU
-//     (src/cuda/orb_gaussian.cu:21-138), ORB_compute_descriptorGPU (src/cuda/orb_descriptor.cu:12-69),
-//     ORB_copy_output_GPU (src/cuda/orb_copy_output.cu:12-45) and the D2D descriptor copies
-//     (src/cuda/orb_gpu.cpp:819-831).
+// K4  k_orient_desc: one warp per keypoint.  Intensity-centroid angle from the level image (lanes =
+//     columns of the radius-15 disc), then the 37x37 window of the BLURRED level around the keypoint is
+//     staged in shared memory (40-byte rows, aligned words) and the 256 steered BRIEF tests sample it;
+//     finally the output planes are written at the keypoint's final (compacted) index.
+//     replaces FASTComputeOrientationGPU (src/cuda/orb_FAST_orientation.cu:17-65), ORB_compute_descriptorGPU
+//     (src/cuda/orb_descriptor.cu:12-69), ORB_copy_output_GPU (src/cuda/orb_copy_output.cu:12-45) and the
+//     per-level D2D descriptor copies (src/cuda/orb_gpu.cpp:819-831).
 // =================================================================================================
-__device__ __forceinline__ int blur_at(const uint8_t* pc, const float* __restrict__ gw) {
-    // pc -> staged patch at the sample centre; 49 sequential FFMA, row-major taps, trunc to u8
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = -3; i <= 3; ++i) {
-#pragma unroll
-        for (int j = -3; j <= 3; ++j) acc = __fmaf_rn(gw[(i + 3) * 7 + (j + 3)], (float)pc[i * JSFE_PATCH_PITCH + j], acc);
-    }
-    return (int)(__float2uint_rz(acc) & 0xFFu);
-}
+#define JSFE_DP_R 18      // max |rotated rBRIEF offset|: 13*sqrt(2) = 18.4 -> rint <= 18
+#define JSFE_DP_ROWS 37
+#define JSFE_DP_PITCH 40  // 37 + up to 3 bytes of alignment slack
 
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, int slot0) {
-    __shared__ __align__(16) uint8_t s_patch[8][JSFE_PATCH_ROWS * JSFE_PATCH_PITCH];
-    __shared__ float s_gw[49];
+    __shared__ __align__(16) uint8_t s_patch[8][JSFE_DP_ROWS * JSFE_DP_PITCH];
     __shared__ int8_t s_px[512], s_py[512];
     const int slot = slot0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_px[i] = p.tab->pat_x[i]; s_py[i] = p.tab->pat_y[i]; }
-    if (threadIdx.x < 49) s_gw[threadIdx.x] = p.tab->gauss[threadIdx.x];
-    __syncthreads();
     const int n = p.n_kp[slot];
+    if ((int)blockIdx.x * 8 >= n) return;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_px[i] = p.tab->pat_x[i]; s_py[i] = p.tab->pat_y[i]; }
+    __syncthreads();
     const int o = blockIdx.x * 8 + warp;
     if (o >= n) return;
     const size_t so = (size_t)slot * p.cap + o;
     const int x = p.kp_x[so], y = p.kp_y[so], l = p.kp_l[so], score = p.kp_s[so];
     const LevelGeom& lv = p.lv[l];
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
+    const uint8_t* __restrict__ blr = lv.blur + (size_t)slot * lv.slot_stride;
+
+    // stage the blurred window: rows y-18..y+18, 40 bytes from the aligned address below x-18 (outside = 0)
     uint8_t* patch = s_patch[warp];
-    // stage rows y-21..y+21, 48 bytes starting at the aligned address below x-21
-    const int px0 = (x - JSFE_PATCH_R) & ~3, py0 = y - JSFE_PATCH_R;
-    for (int i = lane; i < JSFE_PATCH_ROWS * (JSFE_PATCH_PITCH / 4); i += 32) {
-        const int row = i / (JSFE_PATCH_PITCH / 4), wv = i - row * (JSFE_PATCH_PITCH / 4);
-        const int gy = py0 + row, gx = px0 + 4 * wv;
+    const int bx0 = (x - JSFE_DP_R) & ~3, by0 = y - JSFE_DP_R;
+    for (int i = lane; i < JSFE_DP_ROWS * (JSFE_DP_PITCH / 4); i += 32) {
+        const int row = i / (JSFE_DP_PITCH / 4), wv = i - row * (JSFE_DP_PITCH / 4);
+        const int gy = by0 + row, gx = bx0 + 4 * wv;
         uint32_t v = 0;
-        if (gy >= 0 && gy < lv.h && gx >= 0 && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx));
-        *reinterpret_cast<uint32_t*>(patch + row * JSFE_PATCH_PITCH + 4 * wv) = v;
+        if (gy >= 0 && gy < lv.h && gx >= 0 && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(blr + (size_t)gy * lv.pitch + gx));
+        *reinterpret_cast<uint32_t*>(patch + row * JSFE_DP_PITCH + 4 * wv) = v;
     }
-    __syncwarp();
-    const uint8_t* ctr = patch + JSFE_PATCH_R * JSFE_PATCH_PITCH + (x - px0);
 
     // intensity centroid over the radius-15 disc (integer moments; any summation order is exact)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = abs(u);
-#pragma unroll 1
-        for (int v = -15; v <= 15; ++v) {
-            if (au <= p.tab->umax[abs(v)]) {
-                const int I = ctr[v * JSFE_PATCH_PITCH + u];
-                m10 += u * I;
-                m01 += v * I;
-            }
+        const uint8_t* ctr = img + (size_t)y * lv.pitch + x + u;
+        int vmax = 0;   // largest |v| whose half-width reaches |u|
+#pragma unroll
+        for (int v = 0; v <= 15; ++v) vmax = (au <= p.tab->umax[v]) ? v : vmax;
+        for (int v = -vmax; v <= vmax; ++v) {
+            const int I = __ldg(ctr + v * lv.pitch);
+            m10 += I;
+            m01 += v * I;
         }
+        m10 *= u;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = atan2f((float)m01, (float)m10);
     const float a = cosf(angle), b = sinf(angle);
+    __syncwarp();
 
     // descriptor byte `lane`: 8 comparisons of blurred samples
+    const uint8_t* ctrb = patch + JSFE_DP_R * JSFE_DP_PITCH + (x - bx0);
     unsigned val = 0;
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
         int t[2];
 #pragma unroll
@@ -329,12 +659,7 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
             const float fpx = (float)s_px[pi], fpy = (float)s_py[pi];
             const int row = (int)rintf(__fmaf_rn(b, fpx, __fmul_rn(a, fpy)));
             const int col = __float2int_rn(__fmaf_rn(a, fpx, -__fmul_rn(b, fpy)));
-            const int sx = x + col, sy = y + row;
-            // the reference blurs only [B, h-B) x [B, w-B); everything else of its blurred image is 0
-            int tv = 0;
-            if (sx >= JSFE_B && sx < lv.w - JSFE_B && sy >= JSFE_B && sy < lv.h - JSFE_B)
-                tv = blur_at(ctr + row * JSFE_PATCH_PITCH + col, s_gw);
-            t[k] = tv;
+            t[k] = ctrb[row * JSFE_DP_PITCH + col];
         }
         val |= (unsigned)(t[0] < t[1]) << i;
     }

@@ -25,6 +25,7 @@ struct LevelGeom {
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
     unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
     uint8_t* img;                    // level image of slot 0
+    uint8_t* blur;                   // 7x7-blurred level image of slot 0 (same pitch/stride; zero outside [B,h-B)x[B,w-B))
     const uint8_t* mask;             // [h][pitch] or nullptr (all pass); shared by all slots
 };
 
@@ -33,6 +34,7 @@ struct DevTables {
     uint32_t lut_bits[2048];   // FAST arc LUT, 1 bit per 16-bit ring mask; bit 0xFFFF = 0
     int umax[16];              // radius-15 disc half-widths
     float gauss[49];           // 7x7 sigma=10 weights, row-major
+    float sep_a[7], sep_b[7];  // separable factors: gauss[i*7+j] ~= sep_a[i]*sep_b[j] (|err| < 4e-9)
     int8_t pat_x[512], pat_y[512];
     uint8_t col_rank[JSFE_MAXL][128];     // column priority of the reference's smem tree (0 wins ties)
     uint8_t col_by_rank[JSFE_MAXL][128];  // inverse permutation
@@ -43,6 +45,7 @@ struct Params {
     int cap;        // max keypoints per slot (= number of NMS cells over all levels)
     int n_tile_rows;  // sum of n_tile_h
     int threshold;  // th_FAST_MAX
+    int compass_mode;  // k_fast_blur_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int H0, W0;
     int pyr_groups_total;             // 4-pixel groups over levels 1..L-1
     int pyr_group_start[JSFE_MAXL + 1];
@@ -61,6 +64,10 @@ struct Params {
     float *u_right, *depth;                           // [slot][cap]
     int *best_idx, *best_dist;                        // [slot][cap]
     int* sad_best;                                    // [slot][cap]: accepted SAD minimum or -1
+    // cross-scale NMS scratch (allocated only when apply_nms_ms): hash table of occupied level-0 pixels
+    int ms_table_size;                                // power of two >= 2*cap
+    int *ms_keys, *ms_sums, *ms_cnts;                 // [slot][ms_table_size]
+    uint8_t* ms_drop;                                 // [slot][cap]
 };
 
 }  // namespace jsfe

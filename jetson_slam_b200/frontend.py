@@ -80,6 +80,7 @@ def lib():
         L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
         L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.jsfe_debug_level_blur.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
         L.jsfe_debug_level_keypoints.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.jsfe_profile_enable.argtypes = [vp, C.c_int]
@@ -208,7 +209,7 @@ class Frontend:
         _check(lib().jsfe_slot_view_get(self._h, slot, C.byref(v)))
         return v
 
-    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms")
+    STAGES = ("k_pyramid", "k_fast_blur_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms")
 
     def profile(self, on=True):
         _check(lib().jsfe_profile_enable(self._h, int(on)))
@@ -228,6 +229,12 @@ class Frontend:
         li = self.levels[level]
         out = np.zeros((li.height, li.width), np.uint8)
         _check(lib().jsfe_debug_level_image(self._h, slot, level, out.ctypes.data))
+        return out
+
+    def level_blur(self, slot, level):
+        li = self.levels[level]
+        out = np.zeros((li.height, li.width), np.uint8)
+        _check(lib().jsfe_debug_level_blur(self._h, slot, level, out.ctypes.data))
         return out
 
     def cells(self, slot):

@@ -44,7 +44,8 @@ def _assert_pair_equal(out, kl, dl, kr, dr, st, tag=""):
 
 
 @pytest.mark.parametrize("name,seed", [("tiny", 0), ("tiny", 1), ("tiny-fixed", 0), ("C1", 0), ("C2", 0), ("C3", 0), ("C4", 0),
-                                       ("KITTI00-02", 0), ("EuRoC", 0), ("C5", 0)])
+                                       ("KITTI00-02", 0), ("EuRoC", 0), ("C5", 0),
+                                       ("KITTI04-12", 0), ("KAIST-nmsms-cpu", 0)])
 def test_stages_match_oracle(name, seed):
     cfg = CONFIGS[name]
     L, R = synth.stereo_pair(cfg.height, cfg.width, seed)
@@ -55,7 +56,9 @@ def test_stages_match_oracle(name, seed):
     for slot, o in ((0, ol), (1, orr)):
         for l in range(cfg.n_levels):
             assert np.array_equal(fe.level_image(slot, l), o.level_image(l)), f"pyramid level {l} slot {slot}"
-        cx, cy, cs = fe.cells(slot)
+            gb, ob = fe.level_blur(slot, l), o.level_blur(l)
+            assert np.array_equal(gb, ob), f"blurred level {l} slot {slot}: {np.count_nonzero(gb != ob)} px differ"
+        cx, cy, cs = fe.cells(slot)  # after the optional cross-scale NMS, as in the oracle
         ox, oy, os_ = o.cells()
         assert np.array_equal(cs, os_), f"cell scores slot {slot}: {np.count_nonzero(cs != os_)} differ"
         pos = os_ > 0
@@ -98,6 +101,30 @@ def test_degenerate_inputs_match_reference_golden():
         k, d = ex.extract(img)
         assert k.shape == g[f"kps_{nm}"].shape and np.array_equal(k, g[f"kps_{nm}"]), nm
         assert np.array_equal(d, g[f"desc_{nm}"]), nm
+
+
+def test_blur_is_exact_on_flat_and_saturated_images():
+    """Constant / two-level / saturated windows put the separable blur value within 1e-5 of an integer, i.e. they all
+    take the exact-chain fallback of k_fast_blur_cells; the stored bytes must still be the reference's."""
+    cfg = CONFIGS["C1"]
+    rng = np.random.default_rng(3)
+    imgs = dict(synth.degenerate_images(cfg.height, cfg.width))
+    imgs["flat200"] = np.full((cfg.height, cfg.width), 200, np.uint8)
+    imgs["blocks"] = (rng.integers(0, 256, size=(cfg.height // 8 + 1, cfg.width // 8 + 1)).astype(np.uint8)
+                      .repeat(8, 0).repeat(8, 1)[:cfg.height, :cfg.width]).copy()
+    imgs["ramp"] = np.tile((np.arange(cfg.width) // 3 % 256).astype(np.uint8), (cfg.height, 1))
+    o = orc.Oracle(**cfg.extractor_kwargs())
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=1)
+    for nm, img in imgs.items():
+        o.extract(img)
+        fe.set_images(np.ascontiguousarray(img))
+        fe.extract(0, 1)
+        for l in range(cfg.n_levels):
+            gb, ob = fe.level_blur(0, l), o.level_blur(l)
+            assert np.array_equal(gb, ob), f"{nm} level {l}: {np.count_nonzero(gb != ob)} blurred px differ"
+        k0, d0 = o.extract(img)
+        k1, d1 = fe.get_keypoints(0)
+        assert np.array_equal(k0, k1) and np.array_equal(d0, d1), nm
 
 
 def test_empty_pair_gives_no_matches():
