@@ -47,7 +47,8 @@ def kernel_algorithmic_bytes(levels_hw, cap, n_mean):
     prest = sum(h * w for h, w in levels_hw[1:])
     return {
         "k_pyramid": p0 + prest,                       # read L0 once, write every resampled level once
-        "k_fast_blur_cells": p0 + prest + 12 * cap,    # read every level once, write (x,y,score) per cell (blurred levels: scratch, not counted)
+        "k_fast_cells": p0 + prest + 12 * cap,         # read every level once, write (x,y,score) per cell
+        "k_blur": 2 * (p0 + prest),                     # read every level once, write its blurred copy (an implementation artefact)
         "k_compact": 12 * cap + 16 * n_mean,           # read cells, write compacted (x,y,score,level)
         "k_orient_desc": n_mean * (31 * 31 + 37 * 37 + 16 + 56 + 4),  # read disc + blurred window + kp, write SoA 24B + desc 32B + angle
         "k_stereo_match": n_mean * (64 + 462 + 8),     # per PAIR: 2 descriptors, two 11x21 strips, uRight+depth

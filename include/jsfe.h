@@ -165,7 +165,7 @@ int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y,
  * stream.  jsfe_profile_read synchronises those events, returns the accumulated milliseconds and launch counts
  * per stage (JSFE_STAGE_*) since the last read, and resets the accumulators. */
 enum { JSFE_STAGE_PYRAMID = 0, JSFE_STAGE_FAST_CELLS = 1, JSFE_STAGE_COMPACT = 2, JSFE_STAGE_ORIENT_DESC = 3,
-       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_NUM_STAGES = 7 };
+       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_STAGE_BLUR = 7, JSFE_NUM_STAGES = 8 };
 int jsfe_profile_enable(jsfe_handle* h, int on);
 int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, int n_stages);
 /* number of kernels the library has launched since creation (bench.py's gpu_launches) */

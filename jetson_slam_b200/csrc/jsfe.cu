@@ -225,6 +225,15 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         if (i >= 1) P.pyr_group_start[i + 1] = P.pyr_group_start[i] + g.h * (g.pitch / 4);
     }
     P.pyr_groups_total = P.L > 1 ? P.pyr_group_start[P.L] : 0;
+    P.blur_item_start[0] = 0;
+    for (int i = 0; i < P.L; ++i) {
+        const jsfe::LevelGeom& g = P.lv[i];
+        int items = 0;
+        if (g.w > 2 * JSFE_B && g.h > 2 * JSFE_B)
+            items = ((g.w - 2 * JSFE_B + 3) / 4) * ((g.h - 2 * JSFE_B + 31) / 32);
+        P.blur_item_start[i + 1] = P.blur_item_start[i] + items;
+    }
+    P.blur_items_total = P.blur_item_start[P.L];
     P.fast_items_total = items;
     P.cap = cells;
     P.n_tile_rows = tile_rows;
@@ -367,8 +376,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         cudaMallocHost((void**)&h->h_dp, M * cap * sizeof(float) + 16) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_misc, 5 * cap * sizeof(int32_t) + 16) != cudaSuccess)
         return bail(fail(JSFE_ERR_CUDA, "pinned host allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-    if (h->fast_smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(jsfe::k_fast_blur_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
+    if (h->fast_smem + 4096 > 48 * 1024) {  // dynamic + static shared memory beyond 48 KB needs the opt-in
+        if (cudaFuncSetAttribute(jsfe::k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
             return bail(fail(JSFE_ERR_CUDA, "k_fast_cells needs %zu bytes of shared memory", h->fast_smem));
     }
     CU(cudaDeviceSynchronize());
@@ -448,9 +457,16 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     }
     {
         StageTimer t(h, st, 1);
-        jsfe::k_fast_blur_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
+        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
     }
-    if ((rc = post_launch(h, "k_fast_blur_cells"))) return rc;
+    if ((rc = post_launch(h, "k_fast_cells"))) return rc;
+    if (P.blur_items_total > 0) {
+        {
+            StageTimer t(h, st, 7);
+            jsfe::k_blur<<<dim3((P.blur_items_total + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+        }
+        if ((rc = post_launch(h, "k_blur"))) return rc;
+    }
     if (h->cfg.apply_nms_ms && P.L > 1) {  // orb_gpu.cpp:665-712
         {
             StageTimer t(h, st, 6);

@@ -59,81 +59,43 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 }
 
 // =================================================================================================
-// K2  k_fast_blur_cells: one block per group of adjacent NMS cells.  The block stages its pixel tile
-//     (+4 px halo) in shared memory once and produces, from that single read of the level image,
-//       (a) FAST ring test + SAD score for every pixel of the group (+1 px halo), kept in shared memory
-//           -- the reference's int32 score map never exists in HBM;
-//       (b) the fused 3x3 NMS and per-cell arg-max under the reference's tie-break order;
-//       (c) the 7x7 sigma=10 blur of the group's pixels (descriptor input).
-//     replaces FASTComputeScoreGPU_patternSize_16_lookup_mask (src/cuda/orb_FAST_compute_score.cu:1412-1560),
-//              Tile_unrolling_reduction_kernel_v2             (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397),
-//              imgaussian_GPU                                 (src/cuda/orb_gaussian.cu:21-138).
+// K2  k_fast_cells: FAST ring test + SAD score + fused 3x3 NMS + per-cell arg-max.  One block owns a
+//     group of adjacent NMS cells, stages their pixels (+4 px halo) in shared memory once and keeps the
+//     scores there -- the reference's int32 score map (and its 9 reads per pixel) never exist in HBM.
+//     replaces FASTComputeScoreGPU_patternSize_16_lookup_mask (src/cuda/orb_FAST_compute_score.cu:1412-1560)
+//          and Tile_unrolling_reduction_kernel_v2              (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397)
 //
-//  FAST is ALU-bound, not HBM-bound, so the work is cut before it is parallelised:
+//  FAST is integer-ALU-bound, not HBM-bound, so the work is cut before it is spread:
 //   phase A  4 pixels per thread, packed-byte SWAR: |p-v| with VABSDIFF4, per-byte compares in the byte
-//            MSBs.  Only the 4 compass ring points are looked at; a pixel survives iff the reference's two
+//            MSBs.  Only the 4 compass ring points are read; a pixel survives iff the reference's two
 //            early-outs do not fire AND enough adjacent compass points are all brighter / all darker for ANY
-//            accepted arc to exist (a necessary condition derived from FAST_N_MIN and verified against the LUT
-//            at create time).  Survivors are appended to a shared-memory work list (warp-aggregated).
-//   phase B  the work list is processed densely (no divergence): full 16-point masks, LUT, SAD.
-//  Every rejected pixel has score 0 in the reference too, so the score tile is bit-identical.
-//
-//  Blur: the reference's value is trunc(chain of 49 sequential FFMA).  We evaluate the separable form
-//  (7+7 FFMA, row sums kept in registers in a 7-deep rotating window, 4 columns per thread) whose distance to
-//  the chain is bounded by 5.3e-4; when the separable value lies within 6e-4 of an
-//  integer the exact chain is evaluated from the staged tile instead.  The stored byte is therefore always
-//  the reference's.
+//            accepted arc to exist (a necessary condition derived from FAST_N_MIN and verified against the
+//            LUT at create time).  Survivors go to a shared-memory work list (ballot-compacted).
+//   phase B  the work list is evaluated densely, 4 ring points per packed word: masks, LUT, SAD (VABSDIFF4.ACC).
+//   phase C  the work list is walked once more: positive scores do the 3x3 NMS test and one shared-memory
+//            atomicMax per cell on a key that encodes the reference's tie-break order:
+//            (score desc, column priority of the reference's smem tree asc, y-lane (y-y0)%T asc, y asc).
+//  Every pixel rejected in phase A has score 0 in the reference too, so scores are bit-identical.
 // =================================================================================================
-#define JSFE_BLUR_EPS 6.0e-4f
 
-// per-byte MSB = (a > b), unsigned bytes; other bits are garbage
-__device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b) {
-    const unsigned t = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
+// per-byte MSB = (a > b), unsigned bytes; nb7 = ~b & 0x7f7f7f7f (hoisted when b is loop-invariant)
+__device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b, unsigned nb7) {
+    const unsigned t = (a & 0x7f7f7f7fu) + nb7;
     return (a & ~b) | (~(a ^ b) & t);
 }
 
-__device__ __forceinline__ int fast_score(const uint8_t* c, int pw, int t, const uint32_t* __restrict__ lut) {
-    const int v = c[0], vt = v + t, v_t = v - t;
-    const int p4 = c[3], p12 = c[-3];
-    if (p4 <= vt && p4 >= v_t && p12 <= vt && p12 >= v_t) return 0;
-    const int p0 = c[3 * pw], p8 = c[-3 * pw];
-    if (p0 <= vt && p0 >= v_t && p8 <= vt && p8 >= v_t) return 0;
-    int r[16];
-    r[0] = p0; r[4] = p4; r[8] = p8; r[12] = p12;
-    r[1] = c[3 * pw + 1];  r[2] = c[2 * pw + 2];   r[3] = c[pw + 3];
-    r[5] = c[-pw + 3];     r[6] = c[-2 * pw + 2];  r[7] = c[-3 * pw + 1];
-    r[9] = c[-3 * pw - 1]; r[10] = c[-2 * pw - 2]; r[11] = c[-pw - 3];
-    r[13] = c[pw - 3];     r[14] = c[2 * pw - 2];  r[15] = c[3 * pw - 1];
-    unsigned bright = 0, dark = 0;
-    int sad = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        bright |= (unsigned)(r[k] > vt) << k;
-        dark |= (unsigned)(r[k] < v_t) << k;
-        sad += abs(r[k] - v);
-    }
-    const unsigned hit = ((__ldg(lut + (bright >> 5)) >> (bright & 31)) | (__ldg(lut + (dark >> 5)) >> (dark & 31))) & 1u;
-    return hit ? sad : 0;
+// scalar reference form, kept for documentation and used by nothing on the hot path
+__device__ __forceinline__ unsigned nibble_of_msbs(unsigned flags) {
+    // gathers bit7 of each byte into bits 0..3 (byte k -> bit k): ((x>>7)&0x01010101) * 0x01020408 >> 24
+    return (((flags >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
-// the reference's blur value: 49 sequential FFMA in row-major tap order, truncated (orb_gaussian.cu:37-135)
-__device__ __forceinline__ unsigned blur_exact(const uint8_t* pc, int pw, const float* __restrict__ gw) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = -3; i <= 3; ++i) {
-#pragma unroll
-        for (int j = -3; j <= 3; ++j) acc = __fmaf_rn(gw[(i + 3) * 7 + (j + 3)], (float)(unsigned)pc[i * pw + j], acc);
-    }
-    return __float2uint_rz(acc) & 0xFFu;
-}
-
-__device__ __forceinline__ float byte_f(unsigned w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
-
-__global__ void __launch_bounds__(256) k_fast_blur_cells(const __grid_constant__ Params p, int slot0) {
+__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, int slot0) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ unsigned s_best[192];
+    __shared__ uint16_t s_colkey[192];   // per owned column: (127 - priority rank) << 8 | cell index
+    __shared__ uint16_t s_rowkey[256];   // per owned row dy: (7 - dy % T) << 8 | (255 - dy)
     __shared__ int s_ncand;
-    __shared__ float s_gw[49];
     int l = 0;
     while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l + 1].block_offset) ++l;
     const LevelGeom& lv = p.lv[l];
@@ -154,7 +116,7 @@ __global__ void __launch_bounds__(256) k_fast_blur_cells(const __grid_constant__
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
 
-    // ---- stage the pixel tile (16-byte vectors; out-of-image = 0), clear scores
+    // ---- stage the pixel tile (16-byte vectors; out-of-image = 0), clear scores, build key tables
     {
         const int vpr = PW >> 4, nvec = PR * vpr;
         for (int i = tid; i < nvec; i += 256) {
@@ -168,214 +130,158 @@ __global__ void __launch_bounds__(256) k_fast_blur_cells(const __grid_constant__
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz = (SR * SW) >> 3;
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
-        if (tid < 192) s_best[tid] = 0;
+        if (tid < 192) {
+            s_best[tid] = 0;
+            if (tid < GW) {
+                const int cell = tid / lv.tile_w, j = tid - cell * lv.tile_w;
+                s_colkey[tid] = (uint16_t)(((127u - p.tab->col_rank[l][j]) << 8) | (unsigned)cell);
+            }
+        }
+        if (tid < lv.tile_h) s_rowkey[tid] = (uint16_t)(((7u - (unsigned)(tid % lv.T)) << 8) | (255u - (unsigned)tid));
         if (tid == 0) s_ncand = 0;
-        if (tid < 49) s_gw[tid] = p.tab->gauss[tid];
     }
     __syncthreads();
 
-    // ---- phase A: compass pre-test, 4 pixels per thread
+    // ---- phase A: compass pre-test, 4 pixels per thread; thread = (column group g, row lane rl)
     {
         const int cs0 = X0 - 1 - gx0;               // smem column of score column 0
         const int g0 = cs0 >> 2, ngx = ((cs0 + GW + 1) >> 2) - g0 + 1;
-        const int total = SR * ngx;
+        int nrl = 256 / ngx;
+        if (nrl < 1) nrl = 1;                       // (ngx <= 50 by construction)
+        const int niter = (SR + nrl - 1) / nrl;     // warp-uniform trip count: the list append is warp-collective
+        const int rl = tid / ngx, g = tid - rl * ngx;
+        const bool active = rl < nrl;
+        const int c = (g0 + g) << 2, xb = gx0 + c;
         const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
+        // column validity mask of this thread's 4 pixels (MSB per byte), hoisted out of the row loop
+        unsigned vmc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vmc |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
+        if (!active) vmc = 0;
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
-        const unsigned nT = ~T4 & 0x7f7f7f7fu;
+        const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
         const int mode = p.compass_mode;
-        const int dq = 256 / ngx, dr = 256 - dq * ngx;
-        int ry = tid / ngx, g = tid - ry * ngx;
-        const int niter = (total + 255) >> 8;   // warp-uniform trip count: the list append below is warp-collective
-        for (int it = 0, i = tid; it < niter; ++it, i += 256) {
+        const unsigned lt = (1u << lane) - 1u;
+        const uint8_t* rp = pix + (size_t)(rl + 3) * PW + c;
+        const int rstep = nrl * PW;
+        int ry = rl;
+        for (int it = 0; it < niter; ++it, ry += nrl, rp += rstep) {
             unsigned pass = 0;
-            int c = 0;
-            if (i < total) {
-                const int y = y0 - 1 + ry;
-                c = (g0 + g) << 2;
-                const int xb = gx0 + c;
-                if (y >= JSFE_B && y < lv.h - JSFE_B && xb + 3 >= xlo && xb <= xhi) {
-                    const uint8_t* rp = pix + (size_t)(ry + 3) * PW + c;
-                    const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
-                    const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
-                    const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
-                    const unsigned P0 = *reinterpret_cast<const unsigned*>(rp + 3 * PW);   // ring 0  (0,+3)
-                    const unsigned P8 = *reinterpret_cast<const unsigned*>(rp - 3 * PW);   // ring 8  (0,-3)
-                    const unsigned P4 = __byte_perm(W1, W2, 0x6543);                       // ring 4  (+3,0)
-                    const unsigned P12 = __byte_perm(W0, W1, 0x4321);                      // ring 12 (-3,0)
-                    const unsigned v = W1;
-                    unsigned d, df0, df4, df8, df12, gt0, gt4, gt8, gt12;
-                    d = __vabsdiffu4(P0, v);  df0 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt0 = msb_gt(P0, v);
-                    d = __vabsdiffu4(P4, v);  df4 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt4 = msb_gt(P4, v);
-                    d = __vabsdiffu4(P8, v);  df8 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT));  gt8 = msb_gt(P8, v);
-                    d = __vabsdiffu4(P12, v); df12 = (d & ~T4) | (~(d ^ T4) & ((d & 0x7f7f7f7fu) + nT)); gt12 = msb_gt(P12, v);
-                    // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
-                    const unsigned rej = (~df4 & ~df12) | (~df0 & ~df8);
+            const int y = y0 - 1 + ry;
+            if (vmc && ry < SR && y >= JSFE_B && y < lv.h - JSFE_B) {
+                const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
+                const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
+                const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
+                const unsigned P0 = *reinterpret_cast<const unsigned*>(rp + 3 * PW);   // ring 0  (0,+3)
+                const unsigned P8 = *reinterpret_cast<const unsigned*>(rp - 3 * PW);   // ring 8  (0,-3)
+                const unsigned P4 = __byte_perm(W1, W2, 0x6543);                       // ring 4  (+3,0)
+                const unsigned P12 = __byte_perm(W0, W1, 0x4321);                      // ring 12 (-3,0)
+                const unsigned v = W1, nv7 = ~v & 0x7f7f7f7fu;
+                const unsigned df0 = msb_gt(__vabsdiffu4(P0, v), T4, nT7), gt0 = msb_gt(P0, v, nv7);
+                const unsigned df4 = msb_gt(__vabsdiffu4(P4, v), T4, nT7), gt4 = msb_gt(P4, v, nv7);
+                const unsigned df8 = msb_gt(__vabsdiffu4(P8, v), T4, nT7), gt8 = msb_gt(P8, v, nv7);
+                const unsigned df12 = msb_gt(__vabsdiffu4(P12, v), T4, nT7), gt12 = msb_gt(P12, v, nv7);
+                // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
+                const unsigned keep = (df4 | df12) & (df0 | df8);
+                unsigned cond;
+                if (mode == 2) {         // an arc of >= 8 covers two ADJACENT compass points: one of {0,8} and one of {4,12}
+                    cond = (((df0 & gt0) | (df8 & gt8)) & ((df4 & gt4) | (df12 & gt12))) |
+                           (((df0 & ~gt0) | (df8 & ~gt8)) & ((df4 & ~gt4) | (df12 & ~gt12)));
+                } else if (mode == 3) {  // three adjacent compass points
                     const unsigned b0 = df0 & gt0, b4 = df4 & gt4, b8 = df8 & gt8, b12 = df12 & gt12;
                     const unsigned k0 = df0 & ~gt0, k4 = df4 & ~gt4, k8 = df8 & ~gt8, k12 = df12 & ~gt12;
-                    unsigned cond;
-                    if (mode == 2) cond = (b0 & b4) | (b4 & b8) | (b8 & b12) | (b12 & b0) | (k0 & k4) | (k4 & k8) | (k8 & k12) | (k12 & k0);
-                    else if (mode == 3) cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
-                                               (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
-                    else if (mode == 1) cond = b0 | b4 | b8 | b12 | k0 | k4 | k8 | k12;
-                    else cond = 0xffffffffu;
-                    pass = cond & ~rej & 0x80808080u;
-                    // column validity (score region, interior) and image mask
-                    unsigned vm = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) vm |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
-                    if (lv.mask != nullptr) {
-                        const unsigned mw = __ldg(reinterpret_cast<const unsigned*>(lv.mask + (size_t)y * lv.pitch + xb));
-                        vm &= msb_gt(mw, 0u);
-                    }
-                    pass &= vm;
+                    cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
+                           (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
+                } else if (mode == 1) {
+                    cond = df0 | df4 | df8 | df12;
+                } else {
+                    cond = 0xffffffffu;
+                }
+                pass = cond & keep & vmc;
+                if (lv.mask != nullptr) {
+                    const unsigned mw = __ldg(reinterpret_cast<const unsigned*>(lv.mask + (size_t)y * lv.pitch + xb));
+                    pass &= msb_gt(mw, 0u, 0x7f7f7f7fu);
                 }
             }
-            // append survivors to the work list (warp-aggregated)
-            const int cnt = __popc(pass);
-            int incl = cnt;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, incl, s);
-                if (lane >= s) incl += n;
-            }
-            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-            int base = 0;
-            if (lane == 31 && wtot) base = atomicAdd(&s_ncand, wtot);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            if (cnt) {
-                int o = base + incl - cnt;
+            // append survivors to the work list: 4 ballots (one per byte position), order within the list is free
+            const unsigned bl0 = __ballot_sync(0xffffffffu, pass & 0x00000080u);
+            const unsigned bl1 = __ballot_sync(0xffffffffu, pass & 0x00008000u);
+            const unsigned bl2 = __ballot_sync(0xffffffffu, pass & 0x00800000u);
+            const unsigned bl3 = __ballot_sync(0xffffffffu, pass & 0x80000000u);
+            const int n0 = __popc(bl0), n1 = n0 + __popc(bl1), n2 = n1 + __popc(bl2), n3 = n2 + __popc(bl3);
+            if (n3) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_ncand, n3);
+                base = __shfl_sync(0xffffffffu, base, 0);
                 const int idx0 = ry * SW + (c - cs0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (pass & (0x80u << (8 * k))) cand[o++] = (uint16_t)(idx0 + k);
+                if (pass & 0x00000080u) cand[base + __popc(bl0 & lt)] = (uint16_t)idx0;
+                if (pass & 0x00008000u) cand[base + n0 + __popc(bl1 & lt)] = (uint16_t)(idx0 + 1);
+                if (pass & 0x00800000u) cand[base + n1 + __popc(bl2 & lt)] = (uint16_t)(idx0 + 2);
+                if (pass & 0x80000000u) cand[base + n2 + __popc(bl3 & lt)] = (uint16_t)(idx0 + 3);
             }
-            g += dr; ry += dq;
-            if (g >= ngx) { g -= ngx; ++ry; }
         }
     }
     __syncthreads();
 
-    // ---- phase B: full ring evaluation of the survivors, dense
+    // ---- phase B: full ring evaluation of the survivors, dense, 4 ring points per packed word
+    const int ncand = s_ncand;
+    const float inv_sw = 1.0f / (float)SW;
     {
-        const int n = s_ncand;
-        const float inv_sw = 1.0f / (float)SW;
-        const uint32_t* lut = p.tab->lut_bits;
-        for (int i = tid; i < n; i += 256) {
+        const uint32_t* __restrict__ lut = p.tab->lut_bits;
+        const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
+        const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
+        const int cs0 = X0 - 1 - gx0;
+        for (int i = tid; i < ncand; i += 256) {
             const int idx = cand[i];
             const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
             const int rx = idx - ry * SW;
-            const int s = fast_score(pix + (size_t)(ry + 3) * PW + (X0 - 1 - gx0 + rx), PW, p.threshold, lut);
-            sc[idx] = (uint16_t)s;
-        }
-    }
-
-    // ---- blur of the pixels this block owns (independent of the scores)
-    {
-        const int xa = max(X0, JSFE_B), xb_ = min(X0 + GW, lv.w - JSFE_B);      // owned x range [xa, xb_)
-        const int ya = max(y0, JSFE_B), yb = min(y0 + lv.tile_h, lv.h - JSFE_B); // owned y range [ya, yb)
-        if (xa < xb_ && ya < yb) {
-            const int cg0 = (xa - gx0) >> 2, ncg = ((xb_ - 1 - gx0) >> 2) - cg0 + 1;
-            int nchunk = 256 / ncg;
-            if (nchunk < 1) nchunk = 1;
-            const int rows = yb - ya;
-            if (nchunk > rows) nchunk = rows;
-            const int rpc = (rows + nchunk - 1) / nchunk;
-            float a[7], b[7];
+            const uint8_t* c = pix + (ry + 3) * PW + (cs0 + rx);
+            const unsigned V = (unsigned)c[0] * 0x01010101u, nV7 = ~V & 0x7f7f7f7fu;
+            // ring point k -> byte k%4 of word k/4   (offsets: orb_FAST_compute_score.cu:24-48)
+            const unsigned R0 = __byte_perm(__byte_perm(c[3 * PW], c[3 * PW + 1], 0x0040), __byte_perm(c[2 * PW + 2], c[PW + 3], 0x0040), 0x5410);
+            const unsigned R1 = __byte_perm(__byte_perm(c[3], c[-PW + 3], 0x0040), __byte_perm(c[-2 * PW + 2], c[-3 * PW + 1], 0x0040), 0x5410);
+            const unsigned R2 = __byte_perm(__byte_perm(c[-3 * PW], c[-3 * PW - 1], 0x0040), __byte_perm(c[-2 * PW - 2], c[-PW - 3], 0x0040), 0x5410);
+            const unsigned R3 = __byte_perm(__byte_perm(c[-3], c[PW - 3], 0x0040), __byte_perm(c[2 * PW - 2], c[3 * PW - 1], 0x0040), 0x5410);
+            unsigned bright = 0, dark = 0, sad = 0;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) { a[k] = p.tab->sep_a[k]; b[k] = p.tab->sep_b[k]; }
-            uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
-            for (int w = tid; w < ncg * nchunk; w += 256) {
-                const int ck = w / ncg, cg = w - ck * ncg;
-                const int r0 = ya + ck * rpc, r1 = min(r0 + rpc, yb);   // output rows [r0, r1)
-                if (r0 >= r1) continue;
-                const int c = (cg0 + cg) << 2;                           // smem column of the 4 outputs
-                const int xg = gx0 + c;
-                const int nin = r1 - r0 + 6;                            // input rows r0-3 .. r1+2
-                const uint8_t* rp = pix + (size_t)(r0 - 3 - gy0) * PW + c;
-                float q[4][7];
-                for (int base = 0; base < nin; base += 7) {
-#pragma unroll
-                    for (int ph = 0; ph < 7; ++ph) {
-                        const int ir = base + ph;
-                        if (ir < nin) {
-                            const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
-                            const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
-                            const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
-                            float f[10];  // pixels c-3 .. c+6
-                            f[0] = byte_f(W0, 1); f[1] = byte_f(W0, 2); f[2] = byte_f(W0, 3);
-                            f[3] = byte_f(W1, 0); f[4] = byte_f(W1, 1); f[5] = byte_f(W1, 2); f[6] = byte_f(W1, 3);
-                            f[7] = byte_f(W2, 0); f[8] = byte_f(W2, 1); f[9] = byte_f(W2, 2);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                float r = 0.0f;
-#pragma unroll
-                                for (int j = 0; j < 7; ++j) r = __fmaf_rn(b[j], f[k + j], r);
-                                q[k][ph] = r;
-                            }
-                            if (ir >= 6) {
-                                const int y = r0 + ir - 6;
-                                unsigned out = 0;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    float A = 0.0f;
-#pragma unroll
-                                    for (int j = 0; j < 7; ++j) A = __fmaf_rn(a[j], q[k][(ph + 1 + j) % 7], A);
-                                    const float fl = floorf(A);
-                                    const float fr = A - fl;
-                                    unsigned v = (unsigned)fl;
-                                    if (fr < JSFE_BLUR_EPS || fr > 1.0f - JSFE_BLUR_EPS)
-                                        v = blur_exact(pix + (size_t)(y - gy0) * PW + c + k, PW, s_gw);
-                                    out |= (v & 0xFFu) << (8 * k);
-                                }
-                                uint8_t* o = dst + (size_t)y * lv.pitch + xg;
-                                if (xg >= xa && xg + 3 < xb_) {
-                                    *reinterpret_cast<unsigned*>(o) = out;
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (xg + k >= xa && xg + k < xb_) o[k] = (uint8_t)(out >> (8 * k));
-                                }
-                            }
-                            rp += PW;
-                        }
-                    }
-                }
+            for (int q = 0; q < 4; ++q) {
+                const unsigned R = q == 0 ? R0 : q == 1 ? R1 : q == 2 ? R2 : R3;
+                sad = __vsadu4(R, V) + sad;
+                const unsigned df = msb_gt(__vabsdiffu4(R, V), T4, nT7), gt = msb_gt(R, V, nV7);
+                bright |= nibble_of_msbs(df & gt) << (4 * q);
+                dark |= nibble_of_msbs(df & ~gt) << (4 * q);
             }
+            bright &= 0xFFFFu;
+            dark &= 0xFFFFu;
+            const unsigned hit = ((__ldg(lut + (bright >> 5)) >> (bright & 31)) | (__ldg(lut + (dark >> 5)) >> (dark & 31))) & 1u;
+            sc[idx] = (uint16_t)(hit ? sad : 0u);
         }
     }
     __syncthreads();
 
-    // ---- NMS + per-cell arg-max under the reference's tie-break order:
-    // (score desc, column priority of the smem tree asc, y-lane (y-y0)%T asc, y asc) packed into one key;
-    // all threads sweep the score tile, the few NMS survivors do one shared-memory atomicMax per cell.
+    // ---- phase C: NMS + per-cell arg-max over the work list
     {
-        const uint8_t* rank = p.tab->col_rank[l];
         const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
-        const int nrow = ymax - ymin;
-        const int wv = min(GW, lv.w - X0);          // valid columns of the group
-        if (nrow > 0 && wv > 0) {
-            const int total = nrow * wv;
-            const int dq = 256 / wv, dr = 256 - dq * wv;
-            int yy = tid / wv, xx = tid - yy * wv;
-            for (int i = tid; i < total; i += 256) {
-                const int y = ymin + yy;
-                const uint16_t* row = sc + (y - (y0 - 1)) * SW + (xx + 1);
-                const int s = row[0];
-                if (s) {
+        const int wv = min(GW, lv.w - X0);          // owned columns actually inside the image
+        for (int i = tid; i < ncand; i += 256) {
+            const int idx = cand[i];
+            const unsigned s = sc[idx];
+            if (s) {
+                const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
+                const int rx = idx - ry * SW;
+                const int dy = ry - 1, xx = rx - 1, y = y0 + dy;
+                if (y >= ymin && y < ymax && xx >= 0 && xx < wv) {
+                    const uint16_t* row = sc + idx;
                     const uint16_t* up = row - SW;
                     const uint16_t* dn = row + SW;
                     const bool ok = s >= up[-1] && s >= up[0] && s >= up[1] && s >= row[-1] && s >= row[1] &&
                                     s >= dn[-1] && s >= dn[0] && s >= dn[1];
                     if (ok) {
-                        const int cell = xx / lv.tile_w, j = xx - cell * lv.tile_w;
-                        const int dy = y - y0;
-                        const unsigned key = ((unsigned)s << 18) | ((127u - rank[j]) << 11) | ((7u - (unsigned)(dy % lv.T)) << 8) |
-                                             (255u - (unsigned)dy);
-                        atomicMax(&s_best[cell], key);
+                        const unsigned ck = s_colkey[xx];
+                        const unsigned key = (s << 18) | ((ck >> 8) << 11) | (unsigned)s_rowkey[dy];
+                        atomicMax(&s_best[ck & 0xFFu], key);
                     }
                 }
-                xx += dr; yy += dq;
-                if (xx >= wv) { xx -= wv; ++yy; }
             }
         }
     }
@@ -394,6 +300,104 @@ __global__ void __launch_bounds__(256) k_fast_blur_cells(const __grid_constant__
         p.cell_x[o] = bx;
         p.cell_y[o] = by;
         p.cell_s[o] = bs;
+    }
+}
+
+// =================================================================================================
+// K2c k_blur: 7x7 sigma=10 blur of every level (descriptor input), interior [20,h-20)x[20,w-20) only; the
+//     rest of the blurred level stays 0 exactly like the reference's never-written border.
+//     replaces imgaussian_GPU (src/cuda/orb_gaussian.cu:21-138).
+//
+//  The reference's value is trunc(chain of 49 sequential FFMA).  We evaluate the separable form
+//  (7+7 FFMA per pixel; one thread owns 4 columns x 32 rows and keeps the row sums of the last 7 input rows
+//  in a rotating register window), whose distance to the chain is bounded by 5.3e-4;
+//  when the separable value lies within 6e-4 of an integer the exact chain is evaluated instead, so the
+//  stored byte is always the reference's.  No shared memory: input words come through L1 (each 32-bit word
+//  of a row is shared by 3 neighbouring threads), bytes are widened with PRMT + FADD (0x4B000000 trick).
+// =================================================================================================
+#define JSFE_BLUR_EPS 6.0e-4f
+#define JSFE_BLUR_ROWS 32
+
+// the reference's blur value: 49 sequential FFMA in row-major tap order, truncated (orb_gaussian.cu:37-135)
+__device__ __forceinline__ unsigned blur_exact(const uint8_t* __restrict__ pc, int pitch, const float* __restrict__ gw) {
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int i = -3; i <= 3; ++i) {
+#pragma unroll
+        for (int j = -3; j <= 3; ++j) acc = __fmaf_rn(__ldg(gw + (i + 3) * 7 + (j + 3)), (float)(unsigned)__ldg(pc + i * pitch + j), acc);
+    }
+    return __float2uint_rz(acc) & 0xFFu;
+}
+
+__device__ __forceinline__ float byte_f(unsigned w, unsigned sel) {   // exact u8 -> f32 without I2F
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, int slot0) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= p.blur_items_total) return;
+    int l = 0;
+    while (l + 1 < p.L && gi >= p.blur_item_start[l + 1]) ++l;
+    const LevelGeom& lv = p.lv[l];
+    const int slot = slot0 + blockIdx.y;
+    const int ncg = (lv.w - 2 * JSFE_B + 3) >> 2;               // 4-column groups over [20, w-20)
+    const int li = gi - p.blur_item_start[l];
+    const int strip = li / ncg, cg = li - strip * ncg;
+    const int xg = JSFE_B + (cg << 2);                           // 20 is a multiple of 4: groups are word-aligned
+    const int r0 = JSFE_B + strip * JSFE_BLUR_ROWS, r1 = min(r0 + JSFE_BLUR_ROWS, lv.h - JSFE_B);
+    const int xend = lv.w - JSFE_B;
+    const uint8_t* __restrict__ src = lv.img + (size_t)slot * lv.slot_stride;
+    uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
+    float a[7], b[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = p.tab->sep_a[k]; b[k] = p.tab->sep_b[k]; }
+    const int nin = r1 - r0 + 6;                                 // input rows r0-3 .. r1+2
+    const uint8_t* rp = src + (size_t)(r0 - 3) * lv.pitch + xg;
+    float q[4][7];
+    for (int base = 0; base < nin; base += 7) {
+#pragma unroll
+        for (int ph = 0; ph < 7; ++ph) {
+            const int ir = base + ph;
+            if (ir < nin) {
+                const unsigned W0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
+                const unsigned W1 = __ldg(reinterpret_cast<const unsigned*>(rp));
+                const unsigned W2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
+                float f[10];  // pixels xg-3 .. xg+6
+                f[0] = byte_f(W0, 0x7441); f[1] = byte_f(W0, 0x7442); f[2] = byte_f(W0, 0x7443);
+                f[3] = byte_f(W1, 0x7440); f[4] = byte_f(W1, 0x7441); f[5] = byte_f(W1, 0x7442); f[6] = byte_f(W1, 0x7443);
+                f[7] = byte_f(W2, 0x7440); f[8] = byte_f(W2, 0x7441); f[9] = byte_f(W2, 0x7442);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float r = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) r = __fmaf_rn(b[j], f[k + j], r);
+                    q[k][ph] = r;
+                }
+                if (ir >= 6) {
+                    const int y = r0 + ir - 6;
+                    unsigned out = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float A = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) A = __fmaf_rn(a[j], q[k][(ph + 1 + j) % 7], A);
+                        unsigned v = __float2uint_rz(A);
+                        if (__float2uint_rz(A - JSFE_BLUR_EPS) != __float2uint_rz(A + JSFE_BLUR_EPS))
+                            v = blur_exact(src + (size_t)y * lv.pitch + xg + k, lv.pitch, p.tab->gauss);
+                        out |= (v & 0xFFu) << (8 * k);
+                    }
+                    uint8_t* o = dst + (size_t)y * lv.pitch + xg;
+                    if (xg + 3 < xend) {
+                        *reinterpret_cast<unsigned*>(o) = out;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (xg + k < xend) o[k] = (uint8_t)(out >> (8 * k));
+                    }
+                }
+                rp += lv.pitch;
+            }
+        }
     }
 }
 

@@ -50,6 +50,8 @@ struct Params {
     int pyr_groups_total;             // 4-pixel groups over levels 1..L-1
     int pyr_group_start[JSFE_MAXL + 1];
     int fast_items_total;             // k_fast_cells work items over all levels
+    int blur_items_total;             // k_blur threads (4 columns x 32 rows each) over all levels
+    int blur_item_start[JSFE_MAXL + 1];
     LevelGeom lv[JSFE_MAXL];
     const DevTables* tab;
     // per-slot arrays, slot stride = cap unless noted

@@ -209,7 +209,7 @@ class Frontend:
         _check(lib().jsfe_slot_view_get(self._h, slot, C.byref(v)))
         return v
 
-    STAGES = ("k_pyramid", "k_fast_blur_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms")
+    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms", "k_blur")
 
     def profile(self, on=True):
         _check(lib().jsfe_profile_enable(self._h, int(on)))
