@@ -154,6 +154,15 @@ typedef struct jsfe_host_results {
 } jsfe_host_results;
 int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_results* out, void* stream);
 
+/* ---- end-to-end batch call with HOST buffers (the call a batch user makes; bench.py's `e2e` times exactly this):
+ * replaces, per pair, the whole hot path of Frame::Frame (src/Frame.cpp:103-122,219): image upload, extract x2,
+ * stereo match, download of keypoints/descriptors/uRight/depth.  `images` = [L0,R0,L1,R1,...] contiguous u8
+ * [2*n_pairs][height][width] (pinned memory recommended).  Internally pipelined in chunks of `chunk_pairs` pairs
+ * (<= 0: default) over three CUDA streams: contiguous H2D | re-pitch + kernels | D2H, so transfers hide behind
+ * compute.  Synchronous: on return `out` points at the handle's pinned result slabs for slots [0, 2*n_pairs). */
+int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
+                            float mb, float mbf, jsfe_host_results* out);
+
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
 /* the 7x7-blurred level (descriptor input); zero outside [20,h-20)x[20,w-20) like the reference's image_gaussian_ */
@@ -165,7 +174,7 @@ int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y,
  * stream.  jsfe_profile_read synchronises those events, returns the accumulated milliseconds and launch counts
  * per stage (JSFE_STAGE_*) since the last read, and resets the accumulators. */
 enum { JSFE_STAGE_PYRAMID = 0, JSFE_STAGE_FAST_CELLS = 1, JSFE_STAGE_COMPACT = 2, JSFE_STAGE_ORIENT_DESC = 3,
-       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_STAGE_BLUR = 7, JSFE_NUM_STAGES = 8 };
+       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_STAGE_BLUR = 7, JSFE_STAGE_BLUR_FIX = 8, JSFE_NUM_STAGES = 9 };
 int jsfe_profile_enable(jsfe_handle* h, int on);
 int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, int n_stages);
 /* number of kernels the library has launched since creation (bench.py's gpu_launches) */

@@ -90,6 +90,10 @@ struct jsfe_handle {
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
+    // end-to-end pipeline (jsfe_process_host_pairs): unpitched H2D staging + three streams
+    uint8_t* d_stage = nullptr;
+    cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done;
 };
 
 namespace {
@@ -178,8 +182,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     }
     int cells = 0, tile_rows = 0, items = 0;
     size_t smem_max = 0;
-    P.pyr_group_start[0] = 0;
-    P.pyr_group_start[1] = 0;
+    P.pyr_block_start[0] = 0;
+    P.pyr_block_start[1] = 0;
     for (int i = 0; i < P.L; ++i) {
         jsfe::LevelGeom& g = P.lv[i];
         g.h = i ? (int)((float)cfg->height * inv[i]) : cfg->height;
@@ -222,9 +226,10 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
         smem_max = std::max(smem_max, pr * pw + 2 * (size_t)(g.tile_h + 2) * sw * 2 + 16);  // pixels + scores + work list
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
-        if (i >= 1) P.pyr_group_start[i + 1] = P.pyr_group_start[i] + g.h * (g.pitch / 4);
+        if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 7) / 8);
+        if (g.w >= 16384 || g.h >= 16384) { delete h; return fail(JSFE_ERR_INVALID, "images larger than 16383 pixels are not supported"); }
     }
-    P.pyr_groups_total = P.L > 1 ? P.pyr_group_start[P.L] : 0;
+    P.pyr_blocks_total = P.L > 1 ? P.pyr_block_start[P.L] : 0;
     P.blur_item_start[0] = 0;
     for (int i = 0; i < P.L; ++i) {
         const jsfe::LevelGeom& g = P.lv[i];
@@ -355,8 +360,10 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         (rc = dev_alloc(h, &P.kps, M * 6 * cap)) || (rc = dev_alloc(h, &P.desc, M * cap * 32)) ||
         (rc = dev_alloc(h, &P.u_right, M * cap)) || (rc = dev_alloc(h, &P.depth, M * cap)) ||
         (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
-        (rc = dev_alloc(h, &P.sad_best, M * cap)))
+        (rc = dev_alloc(h, &P.sad_best, M * cap)) || (rc = dev_alloc(h, &P.fix_count, M)))
         return bail(rc);
+    P.fix_cap = 16384;
+    if ((rc = dev_alloc(h, &P.fix_list, M * (size_t)P.fix_cap))) return bail(rc);
     if (cfg->apply_nms_ms && P.L > 1) {
         int ts = 64;
         while (ts < 2 * P.cap) ts <<= 1;
@@ -392,6 +399,12 @@ int jsfe_destroy(jsfe_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+    if (h->st_comp) cudaStreamDestroy(h->st_comp);
+    if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
+    if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_n) cudaFreeHost(h->h_n);
     if (h->h_kps) cudaFreeHost(h->h_kps);
     if (h->h_desc) cudaFreeHost(h->h_desc);
@@ -450,9 +463,9 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const jsfe::Params& P = h->P;
-    if (P.pyr_groups_total > 0) {
+    if (P.pyr_blocks_total > 0) {
         StageTimer t(h, st, 0);
-        jsfe::k_pyramid<<<dim3((P.pyr_groups_total + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+        jsfe::k_pyramid<<<dim3(P.pyr_blocks_total, n), 256, 0, st>>>(P, first_slot);
         if ((rc = post_launch(h, "k_pyramid"))) return rc;
     }
     {
@@ -466,6 +479,11 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
             jsfe::k_blur<<<dim3((P.blur_items_total + 255) / 256, n), 256, 0, st>>>(P, first_slot);
         }
         if ((rc = post_launch(h, "k_blur"))) return rc;
+        {
+            StageTimer t(h, st, 8);
+            jsfe::k_blur_fix<<<dim3((P.fix_cap + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+        }
+        if ((rc = post_launch(h, "k_blur_fix"))) return rc;
     }
     if (h->cfg.apply_nms_ms && P.L > 1) {  // orb_gpu.cpp:665-712
         {
@@ -635,6 +653,69 @@ int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, 
         h->event_pool.push_back(sp.b);
     }
     h->spans.clear();
+    return JSFE_OK;
+}
+
+int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
+                            float mb, float mbf, jsfe_host_results* out) {
+    int rc = check_slots(h, 0, 2 * n_pairs);
+    if (rc) return rc;
+    if (!images || !out || n_pairs < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(h->device));
+    const jsfe::Params& P = h->P;
+    const jsfe::LevelGeom& g = P.lv[0];
+    const size_t img_bytes = (size_t)g.h * g.w;
+    if (!h->d_stage) {  // first use: staging buffer in the host layout (contiguous rows), streams, events
+        CU(cudaMalloc((void**)&h->d_stage, img_bytes * h->max_images));
+        CU(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    }
+    if (chunk_pairs < 1) chunk_pairs = 32;
+    const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+    while ((int)h->ev_up.size() < n_chunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_up.push_back(a);
+        h->ev_done.push_back(b);
+    }
+    const size_t cap = P.cap;
+    const bool saved_prof = h->profiling;
+    h->profiling = false;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int p0 = c * chunk_pairs, np = std::min(chunk_pairs, n_pairs - p0);
+        const int s0 = 2 * p0, ns = 2 * np;
+        // 1. one contiguous H2D per chunk (2-D copies with odd row widths run far below PCIe speed)
+        CU(cudaMemcpyAsync(h->d_stage + img_bytes * s0, images + img_bytes * s0, img_bytes * ns, cudaMemcpyHostToDevice, h->st_h2d));
+        CU(cudaEventRecord(h->ev_up[c], h->st_h2d));
+        // 2. re-pitch into the slots (device-to-device), extract, match
+        CU(cudaStreamWaitEvent(h->st_comp, h->ev_up[c], 0));
+        if ((rc = jsfe_set_images(h, s0, ns, h->d_stage + img_bytes * s0, g.w, (int64_t)img_bytes, 1, h->st_comp))) break;
+        if ((rc = jsfe_extract(h, s0, ns, h->st_comp))) break;
+        if ((rc = jsfe_stereo_match(h, p0, np, th_high, th_low, mb, mbf, h->st_comp))) break;
+        CU(cudaEventRecord(h->ev_done[c], h->st_comp));
+        // 3. results of this chunk back to pinned host memory while the next chunk computes
+        CU(cudaStreamWaitEvent(h->st_d2h, h->ev_done[c], 0));
+        CU(cudaMemcpyAsync(h->h_n + s0, P.n_kp + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(cudaMemcpyAsync(h->h_kps + (size_t)s0 * 6 * cap, P.kps + (size_t)s0 * 6 * cap, (size_t)ns * 6 * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(cudaMemcpyAsync(h->h_desc + (size_t)s0 * cap * 32, P.desc + (size_t)s0 * cap * 32, (size_t)ns * cap * 32, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(cudaMemcpyAsync(h->h_ur + (size_t)s0 * cap, P.u_right + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
+        CU(cudaMemcpyAsync(h->h_dp + (size_t)s0 * cap, P.depth + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
+    }
+    h->profiling = saved_prof;
+    cudaError_t e1 = cudaStreamSynchronize(h->st_h2d), e2 = cudaStreamSynchronize(h->st_comp), e3 = cudaStreamSynchronize(h->st_d2h);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(JSFE_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+    const size_t N = (size_t)2 * n_pairs;
+    out->n_keypoints = h->h_n;
+    out->kps = h->h_kps;
+    out->desc = h->h_desc;
+    out->u_right = h->h_ur;
+    out->depth = h->h_dp;
+    out->capacity = P.cap;
+    out->bytes = (int64_t)(N * 4 + N * 6 * cap * 4 + N * cap * 32 + 2 * N * cap * 4);
     return JSFE_OK;
 }
 

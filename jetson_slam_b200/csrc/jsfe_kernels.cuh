@@ -16,20 +16,24 @@ namespace jsfe {
 
 // =================================================================================================
 // K1  k_pyramid: every level l >= 1 is a bilinear resample of level 0.
-//     replaces imresize_GPU_pitched (src/cuda/orb_pyramid.cu:18-68), one launch for all levels and
-//     all image slots; one thread = 4 adjacent output pixels = one 32-bit store; pad bytes = 0.
+//     replaces imresize_GPU_pitched (src/cuda/orb_pyramid.cu:18-68): one launch for all levels and all
+//     image slots; a block is a 128 x 8 pixel tile of ONE level (level/tile decode is block-uniform), a
+//     thread produces 4 adjacent pixels = one 32-bit store; pad bytes [w, pitch) are written as 0.
+//     u8->f32 uses the 2^23 magic (LOP + FADD) so that only floor/trunc (F2I) land on the quarter-rate XU pipe.
 // =================================================================================================
+__device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(v | 0x4B000000u) - 8388608.0f; }
+
 __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params p, int slot0) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.pyr_groups_total) return;
     int l = 1;
-    while (l + 1 < p.L && g >= p.pyr_group_start[l + 1]) ++l;
+    while (l + 1 < p.L && (int)blockIdx.x >= p.pyr_block_start[l + 1]) ++l;
     const LevelGeom& lv = p.lv[l];
     const int slot = slot0 + blockIdx.y;
-    const int gl = g - p.pyr_group_start[l];
-    const int gpr = lv.pitch >> 2;  // groups per row
-    const int y = gl / gpr;
-    const int x4 = (gl - y * gpr) << 2;
+    const int bi = blockIdx.x - p.pyr_block_start[l];
+    const int tiles_x = (lv.pitch + 127) >> 7;
+    const int tyb = bi / tiles_x, txb = bi - tyb * tiles_x;
+    const int x4 = (txb << 7) + ((threadIdx.x & 31) << 2);
+    const int y = (tyb << 3) + (threadIdx.x >> 5);
+    if (x4 >= lv.pitch || y >= lv.h) return;
     const uint8_t* __restrict__ src = p.lv[0].img + (size_t)slot * p.lv[0].slot_stride;
     const int sp = p.lv[0].pitch;
     const float s = lv.rscale;
@@ -47,10 +51,10 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
             const int xl = (int)floorf(fx);
             const float wxl = __fsub_rn((float)(xl + 1), fx), wxr = __fsub_rn(1.0f, wxl);
             // FMUL,FMUL,FFMA,FFMA,FFMA,F2I.TRUNC -- the contraction nvcc emits for the reference expression
-            float acc = __fmul_rn(__fmul_rn(wyt, wxr), (float)__ldg(r0 + xl + 1));
-            acc = __fmaf_rn(__fmul_rn(wyt, wxl), (float)__ldg(r0 + xl), acc);
-            acc = __fmaf_rn(__fmul_rn(wyb, wxl), (float)__ldg(r1 + xl), acc);
-            acc = __fmaf_rn(__fmul_rn(wyb, wxr), (float)__ldg(r1 + xl + 1), acc);
+            float acc = __fmul_rn(__fmul_rn(wyt, wxr), u8_to_f32(__ldg(r0 + xl + 1)));
+            acc = __fmaf_rn(__fmul_rn(wyt, wxl), u8_to_f32(__ldg(r0 + xl)), acc);
+            acc = __fmaf_rn(__fmul_rn(wyb, wxl), u8_to_f32(__ldg(r1 + xl)), acc);
+            acc = __fmaf_rn(__fmul_rn(wyb, wxr), u8_to_f32(__ldg(r1 + xl + 1)), acc);
             packed |= (__float2uint_rz(acc) & 0xFFu) << (8 * k);
         }
     }
@@ -138,7 +142,10 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             }
         }
         if (tid < lv.tile_h) s_rowkey[tid] = (uint16_t)(((7u - (unsigned)(tid % lv.T)) << 8) | (255u - (unsigned)tid));
-        if (tid == 0) s_ncand = 0;
+        if (tid == 0) {
+            s_ncand = 0;
+            if (blockIdx.x == 0) p.fix_count[slot] = 0;   // list of k_blur, which runs after this kernel
+        }
     }
     __syncthreads();
 
@@ -148,27 +155,30 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         const int g0 = cs0 >> 2, ngx = ((cs0 + GW + 1) >> 2) - g0 + 1;
         int nrl = 256 / ngx;
         if (nrl < 1) nrl = 1;                       // (ngx <= 50 by construction)
-        const int niter = (SR + nrl - 1) / nrl;     // warp-uniform trip count: the list append is warp-collective
+        // score rows whose y lies in the interior [B, h-B): ry in [ry_lo, ry_hi)
+        const int ry_lo = max(0, JSFE_B - (y0 - 1)), ry_hi = min(SR, lv.h - JSFE_B - (y0 - 1));
+        const int niter = (ry_hi - ry_lo + nrl - 1) / nrl;   // warp-uniform trip count: the list append is warp-collective
         const int rl = tid / ngx, g = tid - rl * ngx;
-        const bool active = rl < nrl;
         const int c = (g0 + g) << 2, xb = gx0 + c;
         const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
         // column validity mask of this thread's 4 pixels (MSB per byte), hoisted out of the row loop
         unsigned vmc = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) vmc |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
-        if (!active) vmc = 0;
+        if (rl >= nrl) vmc = 0;
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
         const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
         const int mode = p.compass_mode;
         const unsigned lt = (1u << lane) - 1u;
-        const uint8_t* rp = pix + (size_t)(rl + 3) * PW + c;
-        const int rstep = nrl * PW;
-        int ry = rl;
-        for (int it = 0; it < niter; ++it, ry += nrl, rp += rstep) {
+        int ry = ry_lo + rl;
+        const uint8_t* rp = pix + (ry + 3) * PW + c;
+        const uint8_t* mp = lv.mask ? lv.mask + (size_t)(y0 - 1 + ry) * lv.pitch + xb : nullptr;
+        int idx0 = ry * SW + (c - cs0);
+        const int rstep = nrl * PW, istep = nrl * SW;
+        const size_t mstep = (size_t)nrl * lv.pitch;
+        for (int it = 0; it < niter; ++it, ry += nrl, rp += rstep, idx0 += istep) {
             unsigned pass = 0;
-            const int y = y0 - 1 + ry;
-            if (vmc && ry < SR && y >= JSFE_B && y < lv.h - JSFE_B) {
+            if (vmc && ry < ry_hi) {
                 const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
                 const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
                 const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
@@ -198,26 +208,25 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                     cond = 0xffffffffu;
                 }
                 pass = cond & keep & vmc;
-                if (lv.mask != nullptr) {
-                    const unsigned mw = __ldg(reinterpret_cast<const unsigned*>(lv.mask + (size_t)y * lv.pitch + xb));
-                    pass &= msb_gt(mw, 0u, 0x7f7f7f7fu);
-                }
+                if (mp != nullptr) pass &= msb_gt(__ldg(reinterpret_cast<const unsigned*>(mp)), 0u, 0x7f7f7f7fu);
             }
-            // append survivors to the work list: 4 ballots (one per byte position), order within the list is free
-            const unsigned bl0 = __ballot_sync(0xffffffffu, pass & 0x00000080u);
-            const unsigned bl1 = __ballot_sync(0xffffffffu, pass & 0x00008000u);
-            const unsigned bl2 = __ballot_sync(0xffffffffu, pass & 0x00800000u);
-            const unsigned bl3 = __ballot_sync(0xffffffffu, pass & 0x80000000u);
-            const int n0 = __popc(bl0), n1 = n0 + __popc(bl1), n2 = n1 + __popc(bl2), n3 = n2 + __popc(bl3);
-            if (n3) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_ncand, n3);
+            if (mp != nullptr) mp += mstep;
+            // append survivors to the work list: exclusive prefix of the per-lane count (0..4) from 3 ballots
+            const unsigned cnt = (((pass >> 7) & 0x01010101u) * 0x01010101u) >> 24;
+            const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u);
+            const unsigned c1 = __ballot_sync(0xffffffffu, cnt & 2u);
+            const unsigned c2 = __ballot_sync(0xffffffffu, cnt & 4u);
+            if (c0 | c1 | c2) {
+                const int pre = __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
+                int base = pre + (int)cnt;                 // lane 31 holds the warp total
+                base = __shfl_sync(0xffffffffu, base, 31);
+                if (lane == 0) base = atomicAdd(&s_ncand, base);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                const int idx0 = ry * SW + (c - cs0);
-                if (pass & 0x00000080u) cand[base + __popc(bl0 & lt)] = (uint16_t)idx0;
-                if (pass & 0x00008000u) cand[base + n0 + __popc(bl1 & lt)] = (uint16_t)(idx0 + 1);
-                if (pass & 0x00800000u) cand[base + n1 + __popc(bl2 & lt)] = (uint16_t)(idx0 + 2);
-                if (pass & 0x80000000u) cand[base + n2 + __popc(bl3 & lt)] = (uint16_t)(idx0 + 3);
+                uint16_t* o = cand + base + pre;
+                if (pass & 0x00000080u) *o++ = (uint16_t)idx0;
+                if (pass & 0x00008000u) *o++ = (uint16_t)(idx0 + 1);
+                if (pass & 0x00800000u) *o++ = (uint16_t)(idx0 + 2);
+                if (pass & 0x80000000u) *o = (uint16_t)(idx0 + 3);
             }
         }
     }
@@ -353,15 +362,23 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
     for (int k = 0; k < 7; ++k) { a[k] = p.tab->sep_a[k]; b[k] = p.tab->sep_b[k]; }
     const int nin = r1 - r0 + 6;                                 // input rows r0-3 .. r1+2
     const uint8_t* rp = src + (size_t)(r0 - 3) * lv.pitch + xg;
+    // software pipeline: the words of the next input row are in flight while this one is consumed
+    unsigned nW0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
+    unsigned nW1 = __ldg(reinterpret_cast<const unsigned*>(rp));
+    unsigned nW2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
     float q[4][7];
     for (int base = 0; base < nin; base += 7) {
 #pragma unroll
         for (int ph = 0; ph < 7; ++ph) {
             const int ir = base + ph;
             if (ir < nin) {
-                const unsigned W0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
-                const unsigned W1 = __ldg(reinterpret_cast<const unsigned*>(rp));
-                const unsigned W2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
+                const unsigned W0 = nW0, W1 = nW1, W2 = nW2;
+                rp += lv.pitch;
+                if (ir + 1 < nin) {
+                    nW0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
+                    nW1 = __ldg(reinterpret_cast<const unsigned*>(rp));
+                    nW2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
+                }
                 float f[10];  // pixels xg-3 .. xg+6
                 f[0] = byte_f(W0, 0x7441); f[1] = byte_f(W0, 0x7442); f[2] = byte_f(W0, 0x7443);
                 f[3] = byte_f(W1, 0x7440); f[4] = byte_f(W1, 0x7441); f[5] = byte_f(W1, 0x7442); f[6] = byte_f(W1, 0x7443);
@@ -375,16 +392,32 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
                 }
                 if (ir >= 6) {
                     const int y = r0 + ir - 6;
-                    unsigned out = 0;
+                    unsigned out = 0, amb = 0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float A = 0.0f;
 #pragma unroll
                         for (int j = 0; j < 7; ++j) A = __fmaf_rn(a[j], q[k][(ph + 1 + j) % 7], A);
-                        unsigned v = __float2uint_rz(A);
-                        if (__float2uint_rz(A - JSFE_BLUR_EPS) != __float2uint_rz(A + JSFE_BLUR_EPS))
-                            v = blur_exact(src + (size_t)y * lv.pitch + xg + k, lv.pitch, p.tab->gauss);
-                        out |= (v & 0xFFu) << (8 * k);
+                        // trunc(A) and |A - nearest integer| without F2I: t = 2^23 + rint(A)
+                        const float t = __fadd_rn(A, 8388608.0f);
+                        const float n = __fsub_rn(t, 8388608.0f);
+                        const unsigned v = (__float_as_uint(t) - (n > A ? 1u : 0u)) & 0xFFu;
+                        amb |= (fabsf(__fsub_rn(A, n)) < JSFE_BLUR_EPS ? 1u : 0u) << k;
+                        out |= v << (8 * k);
+                    }
+                    if (amb) {   // rare (about 0.1 % of pixels): the exact chain decides, later and densely (k_blur_fix)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if ((amb >> k) & 1u) {
+                                const int pos = atomicAdd(p.fix_count + slot, 1);
+                                if (pos < p.fix_cap) {
+                                    p.fix_list[(size_t)slot * p.fix_cap + pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)(xg + k);
+                                } else {  // list full (large flat areas): decide here
+                                    const unsigned v = blur_exact(src + (size_t)y * lv.pitch + xg + k, lv.pitch, p.tab->gauss);
+                                    out = (out & ~(0xFFu << (8 * k))) | (v << (8 * k));
+                                }
+                            }
+                        }
                     }
                     uint8_t* o = dst + (size_t)y * lv.pitch + xg;
                     if (xg + 3 < xend) {
@@ -395,10 +428,24 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
                             if (xg + k < xend) o[k] = (uint8_t)(out >> (8 * k));
                     }
                 }
-                rp += lv.pitch;
             }
         }
     }
+}
+
+// K2d k_blur_fix: the pixels whose separable value was within JSFE_BLUR_EPS of an integer get the reference's
+//     exact 49-FFMA chain, one thread per listed pixel (dense, no divergence).
+__global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ Params p, int slot0) {
+    const int slot = slot0 + blockIdx.y;
+    const int n = min(p.fix_count[slot], p.fix_cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned code = p.fix_list[(size_t)slot * p.fix_cap + i];
+    const int l = code >> 28, y = (code >> 14) & 0x3FFF, x = code & 0x3FFF;
+    const LevelGeom& lv = p.lv[l];
+    if (x >= lv.w - JSFE_B) return;   // pad columns of the last group
+    const uint8_t* src = lv.img + (size_t)slot * lv.slot_stride;
+    lv.blur[(size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x] = (uint8_t)blur_exact(src + (size_t)y * lv.pitch + x, lv.pitch, p.tab->gauss);
 }
 
 // =================================================================================================

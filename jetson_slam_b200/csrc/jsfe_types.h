@@ -47,8 +47,8 @@ struct Params {
     int threshold;  // th_FAST_MAX
     int compass_mode;  // k_fast_blur_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int H0, W0;
-    int pyr_groups_total;             // 4-pixel groups over levels 1..L-1
-    int pyr_group_start[JSFE_MAXL + 1];
+    int pyr_blocks_total;             // k_pyramid blocks (128x8 pixel tiles) over levels 1..L-1
+    int pyr_block_start[JSFE_MAXL + 1];
     int fast_items_total;             // k_fast_cells work items over all levels
     int blur_items_total;             // k_blur threads (4 columns x 32 rows each) over all levels
     int blur_item_start[JSFE_MAXL + 1];
@@ -70,6 +70,10 @@ struct Params {
     int ms_table_size;                                // power of two >= 2*cap
     int *ms_keys, *ms_sums, *ms_cnts;                 // [slot][ms_table_size]
     uint8_t* ms_drop;                                 // [slot][cap]
+    // k_blur -> k_blur_fix: pixels whose separable blur value is too close to an integer
+    int fix_cap;
+    int* fix_count;                                   // [slot]
+    unsigned* fix_list;                               // [slot][fix_cap]: level<<28 | y<<14 | x
 };
 
 }  // namespace jsfe

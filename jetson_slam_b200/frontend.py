@@ -79,6 +79,7 @@ def lib():
         L.jsfe_get_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
+        L.jsfe_process_host_pairs.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(HostResults)]
         L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_level_blur.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -204,12 +205,26 @@ class Frontend:
             "u_right": as_np(r.u_right, (n, cap)), "depth": as_np(r.depth, (n, cap)), "bytes": r.bytes,
         }
 
+    def process_host_pairs(self, images, mb, mbf, chunk_pairs=0, th_high=100, th_low=50):
+        """End-to-end: images u8 [2*n_pairs, H, W] in host memory (L0,R0,L1,R1,...) -> dict of pinned result views.
+        Upload, extract, match and download are pipelined in chunks over three CUDA streams; synchronous."""
+        a = np.asarray(images)
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[1:] != (self.height, self.width) or not a.flags.c_contiguous or a.shape[0] % 2:
+            raise ValueError("images must be C-contiguous uint8 [2*n_pairs, H, W]")
+        n = a.shape[0]
+        r = HostResults()
+        _check(lib().jsfe_process_host_pairs(self._h, n // 2, a.ctypes.data, chunk_pairs, th_high, th_low, mb, mbf, C.byref(r)))
+        cap = r.capacity
+        as_np = np.ctypeslib.as_array
+        return {"n": as_np(r.n_keypoints, (n,)), "kps": as_np(r.kps, (n, 6, cap)), "desc": as_np(r.desc, (n, cap, 32)),
+                "u_right": as_np(r.u_right, (n, cap)), "depth": as_np(r.depth, (n, cap)), "bytes": r.bytes}
+
     def slot_view(self, slot):
         v = SlotView()
         _check(lib().jsfe_slot_view_get(self._h, slot, C.byref(v)))
         return v
 
-    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms", "k_blur")
+    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms", "k_blur", "k_blur_fix")
 
     def profile(self, on=True):
         _check(lib().jsfe_profile_enable(self._h, int(on)))

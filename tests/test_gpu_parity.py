@@ -153,6 +153,18 @@ def test_batch_slots_are_independent_and_order_invariant():
         assert np.array_equal(ur.view(np.int32), ref["u_right"].view(np.int32)) and np.array_equal(bi, ref["best_idx_r"])
     d = fe.download(0, 16)
     assert d["n"][0] == fe.get_keypoints(0)[0].shape[1] and d["bytes"] > 0
+    # the pipelined end-to-end call (host images in, host slabs out) gives the same bytes as the staged calls
+    want = {k: np.array(v) for k, v in d.items() if k != "bytes"}
+    host = np.stack([im for p in pairs for im in p])
+    for chunk in (3, 8):
+        e = fe.process_host_pairs(host, cfg.mb, cfg.mbf, chunk_pairs=chunk)
+        assert np.array_equal(e["n"], want["n"])
+        for s_ in range(16):
+            n = want["n"][s_]
+            assert np.array_equal(e["kps"][s_, :, :n], want["kps"][s_, :, :n]) and np.array_equal(e["desc"][s_, :n], want["desc"][s_, :n])
+            if s_ % 2 == 0:
+                assert np.array_equal(e["u_right"][s_, :n].view(np.int32), want["u_right"][s_, :n].view(np.int32))
+                assert np.array_equal(e["depth"][s_, :n].view(np.int32), want["depth"][s_, :n].view(np.int32))
 
 
 def test_mask_matches_oracle():
