@@ -115,12 +115,14 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture summary (profiles/traffic.json), or None."""
+def ncu_traffic(kernel, units):
+    """DRAM bytes per launch of `kernel`: dram__bytes_read+write per image (per pair for the stereo kernels) from the
+    committed `ncu --set full` capture (profiles/traffic.json), scaled to the units one bench launch processes."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+            per_unit = json.load(open(p)).get(kernel, {}).get("dram_bytes_per_unit")
+            return None if per_unit is None else per_unit * units
         except Exception:
             return None
     return None
@@ -356,7 +358,7 @@ def run_ours(args, cfg):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": per_kernel[dom]["gbs"] / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                         "frac": per_kernel[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, B if dom.startswith("k_stereo") else 2 * B), "peak_source": peak_src,
                          "ms_per_launch": per_kernel[dom]["ms_per_launch"], "share_of_step": per_kernel[dom]["share"]},
             "pipeline_roofline": {"bytes_per_pair": bpp, "achieved": bpp * value / world / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": bpp * value / world / 1e9 / peak},

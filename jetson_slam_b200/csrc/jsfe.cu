@@ -91,6 +91,7 @@ struct jsfe_handle {
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
     // end-to-end pipeline (jsfe_process_host_pairs): unpitched H2D staging + three streams
+    int chunk_images = 0;
     uint8_t* d_stage = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;
@@ -387,6 +388,18 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         if (cudaFuncSetAttribute(jsfe::k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
             return bail(fail(JSFE_ERR_CUDA, "k_fast_cells needs %zu bytes of shared memory", h->fast_smem));
     }
+    {   // sub-batch size: images whose level-0 + levels + blurred levels fit in ~60% of L2
+        size_t per_image = 0;
+        for (int i = 0; i < P.L; ++i) per_image += P.lv[i].slot_stride * (i ? 2 : 1) + (i ? 0 : P.lv[i].slot_stride);
+        int l2 = 0;
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
+        (void)per_image; (void)l2;
+        // Measured on B200 (profiles/r01_chunk_sweep.txt): every kernel of the path is instruction-issue-bound, not
+        // memory-bound, so L2-sized sub-batches only add launch tails (30.5k pairs/s unchunked vs 24.5k..29.5k chunked).
+        // Default: no sub-batching; JSFE_CHUNK_IMAGES overrides for experiments.
+        h->chunk_images = 0;
+        if (const char* e = getenv("JSFE_CHUNK_IMAGES")) h->chunk_images = atoi(e);
+    }
     CU(cudaDeviceSynchronize());
     *out = h;
     return JSFE_OK;
@@ -456,9 +469,21 @@ int jsfe_slot_image(jsfe_handle* h, int slot, uint8_t** dev_ptr, int64_t* pitch)
     return JSFE_OK;
 }
 
+static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream);
+
 int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     int rc = check_slots(h, first_slot, n);
     if (rc) return rc;
+    // Large batches are cut into sub-batches whose pyramid + blurred pyramid stay L2-resident between kernels
+    // (126 MB L2): the levels written by k_pyramid are then read by k_fast_cells / k_blur / k_orient_desc from L2.
+    const int chunk = h->chunk_images > 0 ? h->chunk_images : n;
+    for (int s = 0; s < n; s += chunk)
+        if ((rc = extract_chunk(h, first_slot + s, std::min(chunk, n - s), stream))) return rc;
+    return JSFE_OK;
+}
+
+static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
+    int rc = JSFE_OK;
     if (n == 0) return JSFE_OK;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
