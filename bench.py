@@ -256,9 +256,21 @@ def run_ours(args, cfg):
     fe.set_images(hv, 0, stream)
     stream.synchronize()
 
+    gather = None
+    if args.gather and world > 1:
+        from jetson_slam_b200 import distributed as jd
+        local_slabs = jd.slab_tensors(fe, 0, 2 * B)
+
+        def gather():
+            # NCCL gather of the fixed-capacity result slabs to rank 0, enqueued behind the match kernels
+            with torch.cuda.stream(stream):
+                jd.gather_slabs(local_slabs, world * B, dst=0)
+
     def step_device():
         fe.extract(0, 2 * B, stream)
         fe.stereo_match(cfg.mb, cfg.mbf, 0, B, stream=stream)
+        if gather:
+            gather()
 
     def step_e2e():
         # the public end-to-end call: host images in, host result slabs out (chunked 3-stream pipeline inside)
@@ -352,7 +364,8 @@ def run_ours(args, cfg):
                        "n_levels": cfg.n_levels, "tile": cfg.tile_h, "max_keypoints_per_eye": fe.max_kp,
                        "mean_keypoints_per_eye": n_mean, "stereo_matches_per_step": matched,
                        "distinct_pairs": n_distinct, "l2": "inputs>L2 (%.0f MB of level-0 images per step)" % (2 * B * cfg.height * cfg.width / 1e6),
-                       "parallelism": f"pairs sharded one-batch-per-GPU x{world}, no data-path collective"},
+                       "parallelism": f"pairs sharded one-batch-per-GPU x{world}, no data-path collective" +
+                                      (", NCCL gather of result slabs to rank 0 every step" if gather else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * cfg.height * cfg.width),
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
@@ -386,6 +399,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=32, help="pairs per pipeline chunk of the end-to-end call")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="N>1: also gather every rank's result slabs to rank 0 (NCCL) each step")
     args = ap.parse_args()
     from jetson_slam_b200.configs import CONFIGS
     cfg = CONFIGS[args.workload]
