@@ -123,6 +123,12 @@ int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream);
 int jsfe_stereo_match(jsfe_handle* h, int first_pair, int n, int th_high, int th_low, float mb, float mbf,
                       void* stream);
 
+/* Same, for ONE pair whose eyes live in two handles with identical geometry on the same device (the reference keeps one
+ * ORBExtractor per eye and hands both pyramids to the matcher, src/Frame.cpp:784-800): left = (hl, slot_l), right =
+ * (hr, slot_r).  Results land in hl's slot_l.  `stream` must be ordered after both extractions. */
+int jsfe_stereo_match_cross(jsfe_handle* hl, int slot_l, jsfe_handle* hr, int slot_r, int th_high, int th_low, float mb,
+                            float mbf, void* stream);
+
 /* ---- results */
 int jsfe_slot_view_get(const jsfe_handle* h, int slot, jsfe_slot_view* out);
 /* Level image left on the device by the last extract: replaces the public ORB_GPU::image_
@@ -137,6 +143,9 @@ int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t*
 /* Host copies (synchronise `stream`).  kps_host: 6*N ints with stride N (reference layout), desc_host 32*N;
  * either may be NULL.  Capacity of the host buffers must be jsfe_max_keypoints(). */
 int jsfe_get_keypoints(jsfe_handle* h, int slot, int32_t* kps_host, uint8_t* desc_host, int32_t* n_out, void* stream);
+/* jsfe_get_stereo reads the LEFT slot 2*pair; jsfe_get_stereo_slot reads an explicit left slot (cross-handle use). */
+int jsfe_get_stereo_slot(jsfe_handle* h, int left_slot, float* u_right_host, float* depth_host, int32_t* best_idx_r_host,
+                         int32_t* best_dist_host, int32_t* n_left_out, void* stream);
 int jsfe_get_stereo(jsfe_handle* h, int pair, float* u_right_host, float* depth_host, int32_t* best_idx_r_host,
                     int32_t* best_dist_host, int32_t* n_left_out, void* stream);
 

@@ -531,23 +531,55 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     return JSFE_OK;
 }
 
+namespace {
+jsfe::RightSide right_side_of(const jsfe_handle* hr, int left_mul, int left_add, int right_mul, int right_add) {
+    jsfe::RightSide r;
+    memset(&r, 0, sizeof r);
+    r.kps = hr->P.kps;
+    r.desc = hr->P.desc;
+    r.row_start = hr->P.row_start;
+    for (int i = 0; i < hr->P.L; ++i) r.img[i] = hr->P.lv[i].img;
+    r.left_mul = left_mul; r.left_add = left_add; r.right_mul = right_mul; r.right_add = right_add;
+    return r;
+}
+
+int launch_stereo(jsfe_handle* h, const jsfe::RightSide& r, int first_pair, int n, int th_high, int th_low, float mb, float mbf, cudaStream_t st) {
+    int rc;
+    const jsfe::Params& P = h->P;
+    {
+        StageTimer t(h, st, 4);
+        jsfe::k_stereo_match<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, r, first_pair, th_high, th_low, mb, mbf);
+    }
+    if ((rc = post_launch(h, "k_stereo_match"))) return rc;
+    StageTimer t(h, st, 5);
+    jsfe::k_stereo_outlier<<<n, 1024, 0, st>>>(P, first_pair, r.left_mul, r.left_add);
+    return post_launch(h, "k_stereo_outlier");
+}
+}  // namespace
+
 int jsfe_stereo_match(jsfe_handle* h, int first_pair, int n, int th_high, int th_low, float mb, float mbf, void* stream) {
     int rc = check_slots(h, 2 * first_pair, 2 * n);
     if (rc) return rc;
     if (n == 0) return JSFE_OK;
     if (!(mb > 0.0f) || th_high < 0 || th_high > 32767) return fail(JSFE_ERR_INVALID, "bad stereo parameters");
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const jsfe::Params& P = h->P;
-    {
-        StageTimer t(h, st, 4);
-        jsfe::k_stereo_match<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, first_pair, th_high, th_low, mb, mbf);
-    }
-    if ((rc = post_launch(h, "k_stereo_match"))) return rc;
-    StageTimer t(h, st, 5);
-    jsfe::k_stereo_outlier<<<n, 1024, 0, st>>>(P, first_pair);
-    if ((rc = post_launch(h, "k_stereo_outlier"))) return rc;
-    return JSFE_OK;
+    return launch_stereo(h, right_side_of(h, 2, 0, 2, 1), first_pair, n, th_high, th_low, mb, mbf, (cudaStream_t)stream);
+}
+
+int jsfe_stereo_match_cross(jsfe_handle* hl, int slot_l, jsfe_handle* hr, int slot_r, int th_high, int th_low, float mb, float mbf,
+                            void* stream) {
+    int rc = check_slots(hl, slot_l, 1);
+    if (rc) return rc;
+    if ((rc = check_slots(hr, slot_r, 1))) return rc;
+    if (!(mb > 0.0f) || th_high < 0 || th_high > 32767) return fail(JSFE_ERR_INVALID, "bad stereo parameters");
+    const jsfe::Params &A = hl->P, &B = hr->P;
+    bool same = hl->device == hr->device && A.L == B.L && A.cap == B.cap && A.n_tile_rows == B.n_tile_rows;
+    for (int i = 0; same && i < A.L; ++i)
+        same = A.lv[i].h == B.lv[i].h && A.lv[i].w == B.lv[i].w && A.lv[i].pitch == B.lv[i].pitch &&
+               A.lv[i].slot_stride == B.lv[i].slot_stride && A.lv[i].tile_h == B.lv[i].tile_h && A.lv[i].tile_w == B.lv[i].tile_w;
+    if (!same) return fail(JSFE_ERR_INVALID, "left and right handles must share device and geometry");
+    CU(cudaSetDevice(hl->device));
+    return launch_stereo(hl, right_side_of(hr, 0, slot_l, 0, slot_r), 0, 1, th_high, th_low, mb, mbf, (cudaStream_t)stream);
 }
 
 int jsfe_slot_view_get(const jsfe_handle* h, int slot, jsfe_slot_view* out) {
@@ -618,9 +650,16 @@ int jsfe_get_stereo(jsfe_handle* h, int pair, float* u_right_host, float* depth_
                     int32_t* best_dist_host, int32_t* n_left_out, void* stream) {
     int rc = check_slots(h, 2 * pair, 2);
     if (rc) return rc;
+    return jsfe_get_stereo_slot(h, 2 * pair, u_right_host, depth_host, best_idx_r_host, best_dist_host, n_left_out, stream);
+}
+
+int jsfe_get_stereo_slot(jsfe_handle* h, int left_slot, float* u_right_host, float* depth_host, int32_t* best_idx_r_host,
+                         int32_t* best_dist_host, int32_t* n_left_out, void* stream) {
+    int rc = check_slots(h, left_slot, 1);
+    if (rc) return rc;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t cap = h->P.cap, s = (size_t)2 * pair;
+    const size_t cap = h->P.cap, s = (size_t)left_slot;
     CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + s, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->h_misc, h->P.u_right + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->h_misc + cap, h->P.depth + s * cap, cap * 4, cudaMemcpyDeviceToHost, st));

@@ -737,17 +737,17 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
 //     replaces the host loops + ORBGetDistanceStereoGPU + Compute_L1_distance_GPU + cublasSgemv of
 //     ORB_GPU::ORB_compute_stereo_match (src/cuda/orb_stereo_match.cu:105-561).
 // =================================================================================================
-__global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Params p, int pair0, int th_high, int th_low,
-                                                      float mb, float mbf) {
+__global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Params p, const __grid_constant__ RightSide rsd,
+                                                      int pair0, int th_high, int th_low, float mb, float mbf) {
     const int pair = pair0 + blockIdx.y;
-    const int sl = 2 * pair, sr = sl + 1;
+    const int sl = rsd.left_mul * pair + rsd.left_add, sr = rsd.right_mul * pair + rsd.right_add;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
     const int nL = p.n_kp[sl];
     if (i >= nL) return;
     const int cap = p.cap;
     const int* kL = p.kps + (size_t)sl * 6 * cap;
-    const int* kR = p.kps + (size_t)sr * 6 * cap;
+    const int* kR = rsd.kps + (size_t)sr * 6 * cap;
     const size_t oL = (size_t)sl * cap + i;
     const int XL = kL[i], YL = kL[cap + i], lvl = kL[4 * cap + i];
     const float uL = (float)XL;
@@ -757,8 +757,8 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Pa
     // left descriptor in registers (every lane holds all 8 words)
     const uint4* dl = reinterpret_cast<const uint4*>(p.desc + oL * 32);
     const uint4 l0 = __ldg(dl), l1 = __ldg(dl + 1);
-    const uint8_t* descR = p.desc + (size_t)sr * cap * 32;
-    const int* rs = p.row_start + (size_t)sr * (p.n_tile_rows + 1);
+    const uint8_t* descR = rsd.desc + (size_t)sr * cap * 32;
+    const int* rs = rsd.row_start + (size_t)sr * (p.n_tile_rows + 1);
 
     unsigned best = ((unsigned)th_high << 16) | 0xFFFFu;  // strict-min scan from TH_HIGH; ties -> lowest right index
     for (int lr = max(0, lvl - 1); lr <= min(p.L - 1, lvl + 1); ++lr) {
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Pa
         const float svL = roundf(__fmul_rn((float)YL, inv));
         if (!(suR0 - 10.0f < 0.0f || suR0 + 10.0f >= (float)g.w)) {
             const uint8_t* imL = g.img + (size_t)sl * g.slot_stride + (size_t)(int)svL * g.pitch + (int)suL;
-            const uint8_t* imR = g.img + (size_t)sr * g.slot_stride + (size_t)(int)svL * g.pitch + (int)suR0;
+            const uint8_t* imR = rsd.img[lvl] + (size_t)sr * g.slot_stride + (size_t)(int)svL * g.pitch + (int)suR0;
             const int lc = imL[0];
             int rc[11];
 #pragma unroll
@@ -856,10 +856,10 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Pa
 // K6  k_stereo_outlier: median-of-SAD cut (src/cuda/orb_stereo_match.cu:565-578): drop matches whose SAD
 //     minimum is >= 1.5*1.4*median, median = element n/2 of the ascending list.  Two-pass 8-bit radix
 //     select in shared memory, one block per pair.
-__global__ void __launch_bounds__(1024) k_stereo_outlier(const __grid_constant__ Params p, int pair0) {
+__global__ void __launch_bounds__(1024) k_stereo_outlier(const __grid_constant__ Params p, int pair0, int left_mul, int left_add) {
     __shared__ int hist[256];
     __shared__ int s_n, s_hi, s_k2, s_med;
-    const int sl = 2 * (pair0 + blockIdx.x);
+    const int sl = left_mul * (pair0 + blockIdx.x) + left_add;
     const int nL = p.n_kp[sl];
     const int* sad = p.sad_best + (size_t)sl * p.cap;
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;

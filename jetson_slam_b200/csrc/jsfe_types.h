@@ -76,6 +76,16 @@ struct Params {
     unsigned* fix_list;                               // [slot][fix_cap]: level<<28 | y<<14 | x
 };
 
+// The right eye of a stereo match: normally slots 2p+1 of the same handle (left = 2p), or a slot of ANOTHER handle
+// with identical geometry (the reference keeps one extractor per eye).
+struct RightSide {
+    const int* kps;          // [slot][6][cap]
+    const uint8_t* desc;     // [slot][cap][32]
+    const int* row_start;    // [slot][n_tile_rows + 1]
+    const uint8_t* img[JSFE_MAXL];
+    int left_mul, left_add, right_mul, right_add;   // slot = mul * pair + add
+};
+
 }  // namespace jsfe
 
 #endif

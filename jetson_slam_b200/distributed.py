@@ -45,9 +45,26 @@ def slab_tensors(fe, first_slot: int, n_slots: int) -> dict[str, torch.Tensor]:
     }
 
 
+_PERM_CACHE: dict = {}
+
+
+def _slot_permutation(n_pairs: int, world: int, device) -> torch.Tensor:
+    """Index into the rank-major stack [world * 2*cap_pairs] that yields global pair order [2*n_pairs]."""
+    key = (n_pairs, world, str(device))
+    if key not in _PERM_CACHE:
+        cap_pairs = local_capacity(n_pairs, world)
+        perm = np.empty(2 * n_pairs, np.int64)
+        for r in range(world):
+            for j, p in enumerate(shard_pairs(n_pairs, world, r)):
+                base = (r * cap_pairs + j) * 2
+                perm[2 * p], perm[2 * p + 1] = base, base + 1
+        _PERM_CACHE[key] = torch.from_numpy(perm).to(device)
+    return _PERM_CACHE[key]
+
+
 def gather_slabs(local: dict[str, torch.Tensor], n_pairs: int, dst: int = 0, group=None) -> dict[str, torch.Tensor] | None:
-    """Gather per-rank slabs (leading dim = 2 * local_capacity slots, pair-major L,R) to rank `dst` and reorder them
-    into global pair order.  Returns the assembled dict on `dst`, None elsewhere."""
+    """Gather per-rank slabs (leading dim = 2 * local_capacity slots, pair-major L,R) to rank `dst` and put them in
+    global pair order: one collective and one index_select per array.  Returns the dict on `dst`, None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     cap_pairs = local_capacity(n_pairs, world)
@@ -55,15 +72,12 @@ def gather_slabs(local: dict[str, torch.Tensor], n_pairs: int, dst: int = 0, gro
     for k in SLAB_KEYS:
         t = local[k]
         assert t.shape[0] == 2 * cap_pairs, f"{k}: leading dim {t.shape[0]} != 2*{cap_pairs}"
-        bufs = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+        stacked = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device) if rank == dst else None
+        bufs = list(stacked.unbind(0)) if rank == dst else None
         dist.gather(t.contiguous(), bufs, dst=dst, group=group)
         if rank == dst:
-            full = torch.empty((2 * n_pairs,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            for r in range(world):
-                owned = shard_pairs(n_pairs, world, r)
-                for j, p in enumerate(owned):
-                    full[2 * p: 2 * p + 2] = bufs[r][2 * j: 2 * j + 2]
-            out[k] = full
+            flat = stacked.reshape((world * 2 * cap_pairs,) + tuple(t.shape[1:]))
+            out[k] = flat.index_select(0, _slot_permutation(n_pairs, world, t.device))
     return out if rank == dst else None
 
 
