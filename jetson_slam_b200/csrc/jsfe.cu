@@ -71,6 +71,7 @@ void column_rank(int tile_w, uint8_t* rank, uint8_t* by_rank) {
 }  // namespace
 
 struct jsfe_handle {
+    jsfe::TmaMaps tma;    // TMA descriptors (second __grid_constant__ kernel parameter)
     jsfe_config cfg;
     int device = 0;
     int max_images = 0;
@@ -168,6 +169,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     h->max_images = cfg->max_images;
     jsfe::Params& P = h->P;
     memset(&P, 0, sizeof P);
+    memset(&h->tma, 0, sizeof h->tma);
     P.L = cfg->n_levels;
     P.threshold = cfg->th_fast_max;  // the reference overwrites th_FAST_MIN_ and uses th_FAST_MAX only (orb_gpu.cpp:42-47)
     P.H0 = cfg->height;
@@ -223,7 +225,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         g.block_offset = items;
         items += g.blocks_per_row * g.n_tile_h;
         const size_t gw = (size_t)g.cells_per_block * g.tile_w;
-        const size_t pw = align_up(gw + 8 + 16, 16), pr = g.tile_h + 8;
+        const size_t pw = align_up(gw + 8 + 15, 16), pr = g.tile_h + 8;   // covers X0+GW+4-gx0 with gx0 = floor16(X0-4)
+        g.tile_pw = (int)pw;
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
         smem_max = std::max(smem_max, pr * pw + 2 * (size_t)(g.tile_h + 2) * sw * 2 + 16);  // pixels + scores + work list
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
@@ -351,6 +354,32 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             if ((rc = dev_alloc(h, &dm, m.size())) != JSFE_OK) return bail(rc);
             if (cudaMemcpy(dm, m.data(), m.size(), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(JSFE_ERR_CUDA, "mask upload failed"));
             g.mask = dm;
+        }
+    }
+    // ---- TMA descriptors: 3-D u8 tensors {pitch, h, slots} over every level image / blurred level
+    P.use_tma = (getenv("JSFE_NO_TMA") && atoi(getenv("JSFE_NO_TMA"))) ? 0 : 1;
+    for (int i = 0; i < P.L && P.use_tma; ++i)
+        if (P.lv[i].tile_h + 8 > 256 || P.lv[i].tile_pw > 256) P.use_tma = 0;   // box extents are limited to 256
+    if (P.use_tma) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return bail(fail(JSFE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver"));
+        auto encode = [&](CUtensorMap* m, void* base, const jsfe::LevelGeom& g, unsigned bw, unsigned bh) -> bool {
+            const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.h, (cuuint64_t)M};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.slot_stride};
+            const cuuint32_t box[3] = {bw, bh, 1}, estr[3] = {1, 1, 1};
+            return ((encode_fn)fn)(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        for (int i = 0; i < P.L; ++i) {
+            const jsfe::LevelGeom& g = P.lv[i];
+            if (!encode(&h->tma.tile[i], g.img, g, (unsigned)g.tile_pw, (unsigned)(g.tile_h + 8)) ||
+                !encode(&h->tma.disc[i], g.img, g, 48, 31) || !encode(&h->tma.win[i], g.blur, g, 64, 37))
+                return bail(fail(JSFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d", i));
         }
     }
     // ---- per-slot arrays
@@ -495,7 +524,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     }
     {
         StageTimer t(h, st, 1);
-        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, first_slot);
+        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, h->tma, first_slot);
     }
     if ((rc = post_launch(h, "k_fast_cells"))) return rc;
     if (P.blur_items_total > 0) {
@@ -525,7 +554,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     if ((rc = post_launch(h, "k_compact"))) return rc;
     {
         StageTimer t(h, st, 3);
-        jsfe::k_orient_desc<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, first_slot);
+        jsfe::k_orient_desc<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, h->tma, first_slot);
     }
     if ((rc = post_launch(h, "k_orient_desc"))) return rc;
     return JSFE_OK;

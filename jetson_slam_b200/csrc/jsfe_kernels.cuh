@@ -14,6 +14,30 @@
 
 namespace jsfe {
 
+// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG + SYNCS) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled load: box at element coordinates (x, y, z) of the tensor described by `map` -> dense rows in shared memory
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // =================================================================================================
 // K1  k_pyramid: every level l >= 1 is a bilinear resample of level 0.
 //     replaces imresize_GPU_pitched (src/cuda/orb_pyramid.cu:18-68): one launch for all levels and all
@@ -94,8 +118,9 @@ __device__ __forceinline__ unsigned nibble_of_msbs(unsigned flags) {
     return (((flags >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
-__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, int slot0) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_best[192];
     __shared__ uint16_t s_colkey[192];   // per owned column: (127 - priority rank) << 8 | cell index
     __shared__ uint16_t s_rowkey[256];   // per owned row dy: (7 - dy % T) << 8 | (255 - dy)
@@ -111,7 +136,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int X0 = tx0 * lv.tile_w, GW = ncells * lv.tile_w, y0 = ty * lv.tile_h;
     const int gx0 = ((X0 - 4) >> 4) << 4, gy0 = y0 - 4;
     const int PR = lv.tile_h + 8;
-    const int PW = ((X0 + GW + 4 - gx0) + 15) & ~15;
+    const int PW = lv.tile_pw;          // fixed per level (= TMA box width); covers X0+GW+4-gx0 for every block
     const int SW = (GW + 2 + 7) & ~7;   // score row length (u16), multiple of 8 -> rows are 16-byte aligned
     const int SR = lv.tile_h + 2;
     uint8_t* pix = smem;
@@ -120,8 +145,14 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
 
-    // ---- stage the pixel tile (16-byte vectors; out-of-image = 0), clear scores, build key tables
-    {
+    // ---- stage the pixel tile: one TMA box load (out-of-image rows/columns arrive as 0); meanwhile clear scores, build key tables
+    if (p.use_tma) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)(PR * PW));
+            tma_load_3d(pix, &tm.tile[l], &s_bar, gx0, gy0, slot);
+        }
+    } else {
         const int vpr = PW >> 4, nvec = PR * vpr;
         for (int i = tid; i < nvec; i += 256) {
             const int row = i / vpr, v = i - row * vpr;
@@ -131,6 +162,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * lv.pitch + gx));
             *reinterpret_cast<uint4*>(pix + (size_t)row * PW + (v << 4)) = val;
         }
+    }
+    {
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz = (SR * SW) >> 3;
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
@@ -147,7 +180,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             if (blockIdx.x == 0) p.fix_count[slot] = 0;   // list of k_blur, which runs after this kernel
         }
     }
-    __syncthreads();
+    __syncthreads();                      // also makes the mbarrier init visible to every thread
+    if (p.use_tma) mbar_wait(&s_bar, 0);  // TMA bytes have landed
 
     // ---- phase A: compass pre-test, 4 pixels per thread; thread = (column group g, row lane rl)
     {
@@ -647,46 +681,75 @@ __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params
 // =================================================================================================
 #define JSFE_DP_R 18      // max |rotated rBRIEF offset|: 13*sqrt(2) = 18.4 -> rint <= 18
 #define JSFE_DP_ROWS 37
-#define JSFE_DP_PITCH 40  // 37 + up to 3 bytes of alignment slack
+#define JSFE_DP_PITCH 64  // TMA box {64, 37}: the box origin must be 16-byte aligned in x (measured: unaligned u8 x -> illegal
+                          // instruction), so the box starts at floor16(x-18) and must span 15 + 37 columns
+#define JSFE_DISC_ROWS 31
+#define JSFE_DISC_PITCH 48  // box {48, 31} from floor16(x-15): 15 + 31 columns
+#define JSFE_WIN_BYTES (JSFE_DP_ROWS * JSFE_DP_PITCH)       // 2368
+#define JSFE_DISC_BYTES (JSFE_DISC_ROWS * JSFE_DISC_PITCH)  // 1488
+#define JSFE_WIN_SLOT 2432                                   // 2368 rounded up to 128
+#define JSFE_WARP_SMEM (JSFE_WIN_SLOT + 1536)                // + disc (1488 rounded up to 128)
 
-__global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, int slot0) {
-    __shared__ __align__(16) uint8_t s_patch[8][JSFE_DP_ROWS * JSFE_DP_PITCH];
+__global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
+    __shared__ __align__(128) uint8_t s_buf[8][JSFE_WARP_SMEM];
+    __shared__ __align__(8) uint64_t s_bar[8];
     __shared__ int8_t s_px[512], s_py[512];
     const int slot = slot0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = p.n_kp[slot];
     if ((int)blockIdx.x * 8 >= n) return;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_px[i] = p.tab->pat_x[i]; s_py[i] = p.tab->pat_y[i]; }
-    __syncthreads();
     const int o = blockIdx.x * 8 + warp;
-    if (o >= n) return;
-    const size_t so = (size_t)slot * p.cap + o;
+    const size_t so = (size_t)slot * p.cap + min(o, n - 1);
     const int x = p.kp_x[so], y = p.kp_y[so], l = p.kp_l[so], score = p.kp_s[so];
     const LevelGeom& lv = p.lv[l];
-    const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
-    const uint8_t* __restrict__ blr = lv.blur + (size_t)slot * lv.slot_stride;
-
-    // stage the blurred window: rows y-18..y+18, 40 bytes from the aligned address below x-18 (outside = 0)
-    uint8_t* patch = s_patch[warp];
-    const int bx0 = (x - JSFE_DP_R) & ~3, by0 = y - JSFE_DP_R;
-    for (int i = lane; i < JSFE_DP_ROWS * (JSFE_DP_PITCH / 4); i += 32) {
-        const int row = i / (JSFE_DP_PITCH / 4), wv = i - row * (JSFE_DP_PITCH / 4);
-        const int gy = by0 + row, gx = bx0 + 4 * wv;
-        uint32_t v = 0;
-        if (gy >= 0 && gy < lv.h && gx >= 0 && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(blr + (size_t)gy * lv.pitch + gx));
-        *reinterpret_cast<uint32_t*>(patch + row * JSFE_DP_PITCH + 4 * wv) = v;
+    uint8_t* win = s_buf[warp];                     // blurred window rows y-18..y+18, columns from wx0 (pitch 64)
+    uint8_t* disc = s_buf[warp] + JSFE_WIN_SLOT;    // level image rows y-15..y+15, columns from dx0 (pitch 48)
+    const int wx0 = (x - JSFE_DP_R) & ~15, dx0 = (x - 15) & ~15;   // x >= 20, so both are >= 0
+    if (p.use_tma) {
+        // two TMA box loads per keypoint, issued by one lane; rows/columns outside the image arrive as 0
+        if (lane == 0 && o < n) {
+            mbar_init(&s_bar[warp], 1);
+            mbar_expect_tx(&s_bar[warp], JSFE_WIN_BYTES + JSFE_DISC_BYTES);
+            tma_load_3d(win, &tm.win[l], &s_bar[warp], wx0, y - JSFE_DP_R, slot);
+            tma_load_3d(disc, &tm.disc[l], &s_bar[warp], dx0, y - 15, slot);
+        }
+    }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_px[i] = p.tab->pat_x[i]; s_py[i] = p.tab->pat_y[i]; }
+    __syncthreads();
+    if (o >= n) return;
+    if (p.use_tma) {
+        mbar_wait(&s_bar[warp], 0);
+    } else {
+        const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
+        const uint8_t* __restrict__ blr = lv.blur + (size_t)slot * lv.slot_stride;
+        for (int i = lane; i < JSFE_DP_ROWS * (JSFE_DP_PITCH / 4); i += 32) {
+            const int row = i / (JSFE_DP_PITCH / 4), wv = i - row * (JSFE_DP_PITCH / 4);
+            const int gy = y - JSFE_DP_R + row, gx = wx0 + 4 * wv;
+            uint32_t v = 0;
+            if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(blr + (size_t)gy * lv.pitch + gx));
+            *reinterpret_cast<uint32_t*>(win + row * JSFE_DP_PITCH + 4 * wv) = v;
+        }
+        for (int i = lane; i < JSFE_DISC_ROWS * (JSFE_DISC_PITCH / 4); i += 32) {
+            const int row = i / (JSFE_DISC_PITCH / 4), wv = i - row * (JSFE_DISC_PITCH / 4);
+            const int gy = y - 15 + row, gx = dx0 + 4 * wv;
+            uint32_t v = 0;
+            if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx));
+            *reinterpret_cast<uint32_t*>(disc + row * JSFE_DISC_PITCH + 4 * wv) = v;
+        }
+        __syncwarp();
     }
 
-    // intensity centroid over the radius-15 disc (integer moments; any summation order is exact)
+    // intensity centroid over the radius-15 disc (integer moments; any summation order is exact); lane = column
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = abs(u);
-        const uint8_t* ctr = img + (size_t)y * lv.pitch + x + u;
+        const uint8_t* col = disc + 15 * JSFE_DISC_PITCH + (x - 15 - dx0) + lane;
         int vmax = 0;   // largest |v| whose half-width reaches |u|
 #pragma unroll
         for (int v = 0; v <= 15; ++v) vmax = (au <= p.tab->umax[v]) ? v : vmax;
-        for (int v = -vmax; v <= vmax; ++v) {
-            const int I = __ldg(ctr + v * lv.pitch);
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {
+            const int I = (abs(v) <= vmax) ? (int)col[v * JSFE_DISC_PITCH] : 0;
             m10 += I;
             m01 += v * I;
         }
@@ -696,10 +759,9 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
     m01 = __reduce_add_sync(0xffffffffu, m01);
     const float angle = atan2f((float)m01, (float)m10);
     const float a = cosf(angle), b = sinf(angle);
-    __syncwarp();
 
     // descriptor byte `lane`: 8 comparisons of blurred samples
-    const uint8_t* ctrb = patch + JSFE_DP_R * JSFE_DP_PITCH + (x - bx0);
+    const uint8_t* ctrb = win + JSFE_DP_R * JSFE_DP_PITCH + (x - wx0);
     unsigned val = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -2,6 +2,7 @@
 #ifndef JSFE_TYPES_H
 #define JSFE_TYPES_H
 
+#include <cuda.h>
 #include <stdint.h>
 
 #define JSFE_MAXL 16
@@ -20,6 +21,7 @@ struct LevelGeom {
     int tile_row_offset;             // running sum of n_tile_h (index into row_start)
     int T;                           // y-lanes of the reference's NMS launch (tie-break rule)
     int cells_per_block;             // NMS cells one k_fast_cells block owns (adjacent in a tile row)
+    int tile_pw;                     // shared-memory pixel-tile pitch of k_fast_cells = TMA box width (multiple of 16)
     int blocks_per_row;              // ceil(n_tile_w / cells_per_block)
     int block_offset;                // first k_fast_cells work item of this level
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
@@ -45,7 +47,8 @@ struct Params {
     int cap;        // max keypoints per slot (= number of NMS cells over all levels)
     int n_tile_rows;  // sum of n_tile_h
     int threshold;  // th_FAST_MAX
-    int compass_mode;  // k_fast_blur_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
+    int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
+    int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int H0, W0;
     int pyr_blocks_total;             // k_pyramid blocks (128x8 pixel tiles) over levels 1..L-1
     int pyr_block_start[JSFE_MAXL + 1];
@@ -74,6 +77,17 @@ struct Params {
     int fix_cap;
     int* fix_count;                                   // [slot]
     unsigned* fix_list;                               // [slot][fix_cap]: level<<28 | y<<14 | x
+};
+
+// TMA descriptors (cuTensorMapEncodeTiled, 3-D u8 tensors {pitch, h, slots}), passed as one __grid_constant__ parameter.
+//   tile[l]: box {tile_pw[l], tile_h+8, 1} of level l       -> k_fast_cells pixel tile (+4 px halo), out-of-image = 0
+//   disc[l]: box {48, 31, 1} of level l                      -> k_orient_desc intensity-centroid disc
+//   win[l] : box {64, 37, 1} of the BLURRED level l          -> k_orient_desc rBRIEF sample window
+// Box origins must be 16-byte aligned in x (u8 elements): an unaligned innermost coordinate traps (measured on B200).
+struct TmaMaps {
+    CUtensorMap tile[JSFE_MAXL];
+    CUtensorMap disc[JSFE_MAXL];
+    CUtensorMap win[JSFE_MAXL];
 };
 
 // The right eye of a stereo match: normally slots 2p+1 of the same handle (left = 2p), or a slot of ANOTHER handle
