@@ -230,7 +230,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
         smem_max = std::max(smem_max, pr * pw + 2 * (size_t)(g.tile_h + 2) * sw * 2 + 16);  // pixels + scores + work list
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
-        if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 7) / 8);
+        if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 31) / 32);
         if (g.w >= 16384 || g.h >= 16384) { delete h; return fail(JSFE_ERR_INVALID, "images larger than 16383 pixels are not supported"); }
     }
     P.pyr_blocks_total = P.L > 1 ? P.pyr_block_start[P.L] : 0;
@@ -243,6 +243,15 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         P.blur_item_start[i + 1] = P.blur_item_start[i] + items;
     }
     P.blur_items_total = P.blur_item_start[P.L];
+    P.fix_item_start[0] = 0;
+    for (int i = 0; i < P.L; ++i) {
+        jsfe::LevelGeom& g = P.lv[i];
+        const int ncg = g.w > 2 * JSFE_B ? (g.w - 2 * JSFE_B + 3) / 4 : 0, rows = std::max(0, g.h - 2 * JSFE_B);
+        g.amb_pitch = (int)align_up(std::max(ncg, 1), 16);
+        g.amb_stride = align_up((size_t)g.amb_pitch * std::max(rows, 1), 256);
+        P.fix_item_start[i + 1] = P.fix_item_start[i] + (ncg ? (g.amb_pitch / 16) * rows : 0);
+    }
+    P.fix_items_total = P.fix_item_start[P.L];
     P.fast_items_total = items;
     P.cap = cells;
     P.n_tile_rows = tile_rows;
@@ -329,6 +338,9 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     jsfe::DevTables* dT = nullptr;
     if ((rc = dev_alloc(h, &dT, 1)) != JSFE_OK) return bail(rc);
     if (cudaMemcpy(dT, T, sizeof *T, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(JSFE_ERR_CUDA, "table upload failed"));
+    if (cudaMemcpyToSymbol(jsfe::c_sep_a, T->sep_a, sizeof T->sep_a) != cudaSuccess ||
+        cudaMemcpyToSymbol(jsfe::c_sep_b, T->sep_b, sizeof T->sep_b) != cudaSuccess)
+        return bail(fail(JSFE_ERR_CUDA, "constant upload failed"));
     P.tab = dT;
     delete T;
     T = nullptr;
@@ -339,6 +351,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         jsfe::LevelGeom& g = P.lv[i];
         if ((rc = dev_alloc(h, &g.img, g.slot_stride * M)) != JSFE_OK) return bail(rc);
         if ((rc = dev_alloc(h, &g.blur, g.slot_stride * M)) != JSFE_OK) return bail(rc);  // stays 0 outside the blurred interior
+        if ((rc = dev_alloc(h, &g.amb, g.amb_stride * M)) != JSFE_OK) return bail(rc);    // pad bytes stay 0
         g.mask = nullptr;
         if (cfg->mask) {  // INTER_NEAREST + THRESH_BINARY(10), orb_gpu.cpp:78-90
             std::vector<uint8_t> m((size_t)g.h * g.pitch, 0);
@@ -390,10 +403,10 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         (rc = dev_alloc(h, &P.kps, M * 6 * cap)) || (rc = dev_alloc(h, &P.desc, M * cap * 32)) ||
         (rc = dev_alloc(h, &P.u_right, M * cap)) || (rc = dev_alloc(h, &P.depth, M * cap)) ||
         (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
-        (rc = dev_alloc(h, &P.sad_best, M * cap)) || (rc = dev_alloc(h, &P.fix_count, M)))
+        (rc = dev_alloc(h, &P.sad_best, M * cap)))
         return bail(rc);
-    P.fix_cap = 16384;
-    if ((rc = dev_alloc(h, &P.fix_list, M * (size_t)P.fix_cap))) return bail(rc);
+    P.blur_eps = JSFE_BLUR_EPS;
+    if (const char* e = getenv("JSFE_DEBUG_BLUR_EPS")) P.blur_eps = (float)atof(e);   // experiments only: breaks exactness
     if (cfg->apply_nms_ms && P.L > 1) {
         int ts = 64;
         while (ts < 2 * P.cap) ts <<= 1;
@@ -535,7 +548,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
         if ((rc = post_launch(h, "k_blur"))) return rc;
         {
             StageTimer t(h, st, 8);
-            jsfe::k_blur_fix<<<dim3((P.fix_cap + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+            jsfe::k_blur_fix<<<dim3((P.fix_items_total + 1023) / 1024, n), 256, 0, st>>>(P, first_slot);
         }
         if ((rc = post_launch(h, "k_blur_fix"))) return rc;
     }

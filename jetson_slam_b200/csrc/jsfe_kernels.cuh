@@ -41,11 +41,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // =================================================================================================
 // K1  k_pyramid: every level l >= 1 is a bilinear resample of level 0.
 //     replaces imresize_GPU_pitched (src/cuda/orb_pyramid.cu:18-68): one launch for all levels and all
-//     image slots; a block is a 128 x 8 pixel tile of ONE level (level/tile decode is block-uniform), a
-//     thread produces 4 adjacent pixels = one 32-bit store; pad bytes [w, pitch) are written as 0.
+//     image slots; a block is a 128 x 32 pixel tile of ONE level (level/tile decode is block-uniform); a thread owns
+//     4 adjacent columns (their x terms are computed once) and 4 rows; 4 pixels = one 32-bit store; pad bytes
+//     [w, pitch) are written as 0.
 //     u8->f32 uses the 2^23 magic (LOP + FADD) so that only floor/trunc (F2I) land on the quarter-rate XU pipe.
 // =================================================================================================
 __device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(v | 0x4B000000u) - 8388608.0f; }
+
+#define JSFE_PYR_ROWS 32   // rows per block tile (8 y-lanes x 4 rows each)
 
 __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params p, int slot0) {
     int l = 1;
@@ -56,34 +59,42 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
     const int tiles_x = (lv.pitch + 127) >> 7;
     const int tyb = bi / tiles_x, txb = bi - tyb * tiles_x;
     const int x4 = (txb << 7) + ((threadIdx.x & 31) << 2);
-    const int y = (tyb << 3) + (threadIdx.x >> 5);
-    if (x4 >= lv.pitch || y >= lv.h) return;
+    if (x4 >= lv.pitch) return;
     const uint8_t* __restrict__ src = p.lv[0].img + (size_t)slot * p.lv[0].slot_stride;
     const int sp = p.lv[0].pitch;
     const float s = lv.rscale;
-    const float fy = __fmul_rn(s, (float)y);
-    const int yt = (int)floorf(fy);
-    const float wyt = __fsub_rn((float)(yt + 1), fy), wyb = __fsub_rn(1.0f, wyt);
-    const uint8_t* r0 = src + (size_t)yt * sp;
-    const uint8_t* r1 = r0 + sp;
-    uint32_t packed = 0;
+    // column terms are shared by every row this thread produces
+    int xl[4];
+    float wxl[4], wxr[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int x = x4 + k;
-        if (x < lv.w) {
-            const float fx = __fmul_rn(s, (float)x);
-            const int xl = (int)floorf(fx);
-            const float wxl = __fsub_rn((float)(xl + 1), fx), wxr = __fsub_rn(1.0f, wxl);
+        const float fx = __fmul_rn(s, (float)(x4 + k));
+        xl[k] = (int)floorf(fx);
+        wxl[k] = __fsub_rn((float)(xl[k] + 1), fx);
+        wxr[k] = __fsub_rn(1.0f, wxl[k]);
+        if (x4 + k >= lv.w) { xl[k] = 0; wxl[k] = 0.0f; wxr[k] = 0.0f; }   // pad columns: weights 0 -> byte 0
+    }
+    uint8_t* dst = lv.img + (size_t)slot * lv.slot_stride + x4;
+    const int y_begin = tyb * JSFE_PYR_ROWS + (threadIdx.x >> 5);
+#pragma unroll 2
+    for (int y = y_begin; y < min(lv.h, (tyb + 1) * JSFE_PYR_ROWS); y += 8) {
+        const float fy = __fmul_rn(s, (float)y);
+        const int yt = (int)floorf(fy);
+        const float wyt = __fsub_rn((float)(yt + 1), fy), wyb = __fsub_rn(1.0f, wyt);
+        const uint8_t* r0 = src + (size_t)yt * sp;
+        const uint8_t* r1 = r0 + sp;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
             // FMUL,FMUL,FFMA,FFMA,FFMA,F2I.TRUNC -- the contraction nvcc emits for the reference expression
-            float acc = __fmul_rn(__fmul_rn(wyt, wxr), u8_to_f32(__ldg(r0 + xl + 1)));
-            acc = __fmaf_rn(__fmul_rn(wyt, wxl), u8_to_f32(__ldg(r0 + xl)), acc);
-            acc = __fmaf_rn(__fmul_rn(wyb, wxl), u8_to_f32(__ldg(r1 + xl)), acc);
-            acc = __fmaf_rn(__fmul_rn(wyb, wxr), u8_to_f32(__ldg(r1 + xl + 1)), acc);
+            float acc = __fmul_rn(__fmul_rn(wyt, wxr[k]), u8_to_f32(__ldg(r0 + xl[k] + 1)));
+            acc = __fmaf_rn(__fmul_rn(wyt, wxl[k]), u8_to_f32(__ldg(r0 + xl[k])), acc);
+            acc = __fmaf_rn(__fmul_rn(wyb, wxl[k]), u8_to_f32(__ldg(r1 + xl[k])), acc);
+            acc = __fmaf_rn(__fmul_rn(wyb, wxr[k]), u8_to_f32(__ldg(r1 + xl[k] + 1)), acc);
             packed |= (__float2uint_rz(acc) & 0xFFu) << (8 * k);
         }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * lv.pitch) = packed;
     }
-    uint8_t* dst = lv.img + (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x4;
-    *reinterpret_cast<uint32_t*>(dst) = packed;
 }
 
 // =================================================================================================
@@ -177,7 +188,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         if (tid < lv.tile_h) s_rowkey[tid] = (uint16_t)(((7u - (unsigned)(tid % lv.T)) << 8) | (255u - (unsigned)tid));
         if (tid == 0) {
             s_ncand = 0;
-            if (blockIdx.x == 0) p.fix_count[slot] = 0;   // list of k_blur, which runs after this kernel
         }
     }
     __syncthreads();                      // also makes the mbarrier init visible to every thread
@@ -361,6 +371,11 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
 #define JSFE_BLUR_EPS 6.0e-4f
 #define JSFE_BLUR_ROWS 32
 
+// separable factors of the 7x7 weights; the same for every handle (sigma is fixed at 10 in the reference), kept in
+// constant memory so the FFMAs read them as c[][] operands instead of holding 14 registers (74 -> ~60: 4 blocks/SM)
+__constant__ float c_sep_a[7];
+__constant__ float c_sep_b[7];
+
 // the reference's blur value: 49 sequential FFMA in row-major tap order, truncated (orb_gaussian.cu:37-135)
 __device__ __forceinline__ unsigned blur_exact(const uint8_t* __restrict__ pc, int pitch, const float* __restrict__ gw) {
     float acc = 0.0f;
@@ -376,7 +391,7 @@ __device__ __forceinline__ float byte_f(unsigned w, unsigned sel) {   // exact u
     return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
 }
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, int slot0) {
+__global__ void __launch_bounds__(256, 3) k_blur(const __grid_constant__ Params p, int slot0) {
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= p.blur_items_total) return;
     int l = 0;
@@ -391,28 +406,29 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
     const int xend = lv.w - JSFE_B;
     const uint8_t* __restrict__ src = lv.img + (size_t)slot * lv.slot_stride;
     uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
-    float a[7], b[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { a[k] = p.tab->sep_a[k]; b[k] = p.tab->sep_b[k]; }
+    uint8_t* __restrict__ amap = lv.amb + (size_t)slot * lv.amb_stride;
     const int nin = r1 - r0 + 6;                                 // input rows r0-3 .. r1+2
     const uint8_t* rp = src + (size_t)(r0 - 3) * lv.pitch + xg;
-    // software pipeline: the words of the next input row are in flight while this one is consumed
-    unsigned nW0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
-    unsigned nW1 = __ldg(reinterpret_cast<const unsigned*>(rp));
-    unsigned nW2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
     float q[4][7];
     for (int base = 0; base < nin; base += 7) {
+        // issue the loads of the next 7 input rows back to back (21 independent 32-bit loads in flight per thread):
+        // the rows arrive from L2/HBM while the other warps of the SM are in their FFMA phase
+        unsigned wr[7][3];
+#pragma unroll
+        for (int ph = 0; ph < 7; ++ph) {
+            if (base + ph < nin) {
+                const uint8_t* r = rp + (size_t)ph * lv.pitch;
+                wr[ph][0] = __ldg(reinterpret_cast<const unsigned*>(r - 4));
+                wr[ph][1] = __ldg(reinterpret_cast<const unsigned*>(r));
+                wr[ph][2] = __ldg(reinterpret_cast<const unsigned*>(r + 4));
+            }
+        }
+        rp += (size_t)7 * lv.pitch;
 #pragma unroll
         for (int ph = 0; ph < 7; ++ph) {
             const int ir = base + ph;
             if (ir < nin) {
-                const unsigned W0 = nW0, W1 = nW1, W2 = nW2;
-                rp += lv.pitch;
-                if (ir + 1 < nin) {
-                    nW0 = __ldg(reinterpret_cast<const unsigned*>(rp - 4));
-                    nW1 = __ldg(reinterpret_cast<const unsigned*>(rp));
-                    nW2 = __ldg(reinterpret_cast<const unsigned*>(rp + 4));
-                }
+                const unsigned W0 = wr[ph][0], W1 = wr[ph][1], W2 = wr[ph][2];
                 float f[10];  // pixels xg-3 .. xg+6
                 f[0] = byte_f(W0, 0x7441); f[1] = byte_f(W0, 0x7442); f[2] = byte_f(W0, 0x7443);
                 f[3] = byte_f(W1, 0x7440); f[4] = byte_f(W1, 0x7441); f[5] = byte_f(W1, 0x7442); f[6] = byte_f(W1, 0x7443);
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
                 for (int k = 0; k < 4; ++k) {
                     float r = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 7; ++j) r = __fmaf_rn(b[j], f[k + j], r);
+                    for (int j = 0; j < 7; ++j) r = __fmaf_rn(c_sep_b[j], f[k + j], r);
                     q[k][ph] = r;
                 }
                 if (ir >= 6) {
@@ -431,28 +447,17 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
                     for (int k = 0; k < 4; ++k) {
                         float A = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 7; ++j) A = __fmaf_rn(a[j], q[k][(ph + 1 + j) % 7], A);
+                        for (int j = 0; j < 7; ++j) A = __fmaf_rn(c_sep_a[j], q[k][(ph + 1 + j) % 7], A);
                         // trunc(A) and |A - nearest integer| without F2I: t = 2^23 + rint(A)
                         const float t = __fadd_rn(A, 8388608.0f);
                         const float n = __fsub_rn(t, 8388608.0f);
                         const unsigned v = (__float_as_uint(t) - (n > A ? 1u : 0u)) & 0xFFu;
-                        amb |= (fabsf(__fsub_rn(A, n)) < JSFE_BLUR_EPS ? 1u : 0u) << k;
+                        amb |= (fabsf(__fsub_rn(A, n)) < p.blur_eps ? 1u : 0u) << k;
                         out |= v << (8 * k);
                     }
-                    if (amb) {   // rare (about 0.1 % of pixels): the exact chain decides, later and densely (k_blur_fix)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if ((amb >> k) & 1u) {
-                                const int pos = atomicAdd(p.fix_count + slot, 1);
-                                if (pos < p.fix_cap) {
-                                    p.fix_list[(size_t)slot * p.fix_cap + pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)(xg + k);
-                                } else {  // list full (large flat areas): decide here
-                                    const unsigned v = blur_exact(src + (size_t)y * lv.pitch + xg + k, lv.pitch, p.tab->gauss);
-                                    out = (out & ~(0xFFu << (8 * k))) | (v << (8 * k));
-                                }
-                            }
-                        }
-                    }
+                    // pixels within blur_eps of an integer (about 0.1 % on textured images, all of a flat region) are decided
+                    // by the exact chain in k_blur_fix; here only their 4-bit mask is recorded (dense, no atomics)
+                    amap[(size_t)(y - JSFE_B) * lv.amb_pitch + cg] = (uint8_t)amb;
                     uint8_t* o = dst + (size_t)y * lv.pitch + xg;
                     if (xg + 3 < xend) {
                         *reinterpret_cast<unsigned*>(o) = out;
@@ -467,19 +472,60 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Params p, 
     }
 }
 
-// K2d k_blur_fix: the pixels whose separable value was within JSFE_BLUR_EPS of an integer get the reference's
-//     exact 49-FFMA chain, one thread per listed pixel (dense, no divergence).
+// K2d k_blur_fix: scans the ambiguity masks written by k_blur (16 mask bytes = 64 pixels per load; almost all zero),
+//     compacts the flagged pixels of the block into a shared-memory list and gives each of them the reference's exact
+//     49-FFMA chain, one thread per listed pixel (dense).  When the list is full (flat regions flag whole rows) the
+//     remaining pixels are decided in place -- whole warps are busy then anyway.
+#define JSFE_FIX_VEC 4       // mask vectors per thread
+#define JSFE_FIX_LIST 2048
 __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ Params p, int slot0) {
+    __shared__ unsigned s_list[JSFE_FIX_LIST];
+    __shared__ int s_n;
     const int slot = slot0 + blockIdx.y;
-    const int n = min(p.fix_count[slot], p.fix_cap);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned code = p.fix_list[(size_t)slot * p.fix_cap + i];
-    const int l = code >> 28, y = (code >> 14) & 0x3FFF, x = code & 0x3FFF;
-    const LevelGeom& lv = p.lv[l];
-    if (x >= lv.w - JSFE_B) return;   // pad columns of the last group
-    const uint8_t* src = lv.img + (size_t)slot * lv.slot_stride;
-    lv.blur[(size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x] = (uint8_t)blur_exact(src + (size_t)y * lv.pitch + x, lv.pitch, p.tab->gauss);
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < JSFE_FIX_VEC; ++q) {
+        const int gi = (blockIdx.x * JSFE_FIX_VEC + q) * 256 + threadIdx.x;
+        if (gi >= p.fix_items_total) break;
+        int l = 0;
+        while (l + 1 < p.L && gi >= p.fix_item_start[l + 1]) ++l;
+        const LevelGeom& lv = p.lv[l];
+        const int vpr = lv.amb_pitch >> 4;                            // uint4 vectors per mask row
+        const int li = gi - p.fix_item_start[l];
+        const int row = li / vpr, v = li - row * vpr;
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(lv.amb + (size_t)slot * lv.amb_stride + (size_t)row * lv.amb_pitch) + v);
+        if ((m.x | m.y | m.z | m.w) == 0u) continue;
+        const unsigned words[4] = {m.x, m.y, m.z, m.w};
+        const int y = JSFE_B + row;
+#pragma unroll 1
+        for (int i = 0; i < 16; ++i) {
+            const unsigned bits = (words[i >> 2] >> (8 * (i & 3))) & 0xFu;
+            if (!bits) continue;
+            const int xg = JSFE_B + ((v * 16 + i) << 2);
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const int x = xg + k;
+                if (!((bits >> k) & 1u) || x >= lv.w - JSFE_B) continue;
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < JSFE_FIX_LIST) {
+                    s_list[pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)x;
+                } else {
+                    const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
+                    lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_n, JSFE_FIX_LIST);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const unsigned code = s_list[i];
+        const int l = code >> 28, y = (code >> 14) & 0x3FFF, x = code & 0x3FFF;
+        const LevelGeom& lv = p.lv[l];
+        const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
+        lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
+    }
 }
 
 // =================================================================================================

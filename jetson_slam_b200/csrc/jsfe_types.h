@@ -27,6 +27,9 @@ struct LevelGeom {
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
     unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
     uint8_t* img;                    // level image of slot 0
+    uint8_t* amb;                    // k_blur -> k_blur_fix: 4-bit ambiguity mask per 4-pixel group of the blurred interior
+    int amb_pitch;                   // bytes per mask row (multiple of 16)
+    unsigned long long amb_stride;   // bytes between slots
     uint8_t* blur;                   // 7x7-blurred level image of slot 0 (same pitch/stride; zero outside [B,h-B)x[B,w-B))
     const uint8_t* mask;             // [h][pitch] or nullptr (all pass); shared by all slots
 };
@@ -50,7 +53,7 @@ struct Params {
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
     int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int H0, W0;
-    int pyr_blocks_total;             // k_pyramid blocks (128x8 pixel tiles) over levels 1..L-1
+    int pyr_blocks_total;             // k_pyramid blocks (128x32 pixel tiles) over levels 1..L-1
     int pyr_block_start[JSFE_MAXL + 1];
     int fast_items_total;             // k_fast_cells work items over all levels
     int blur_items_total;             // k_blur threads (4 columns x 32 rows each) over all levels
@@ -73,10 +76,9 @@ struct Params {
     int ms_table_size;                                // power of two >= 2*cap
     int *ms_keys, *ms_sums, *ms_cnts;                 // [slot][ms_table_size]
     uint8_t* ms_drop;                                 // [slot][cap]
-    // k_blur -> k_blur_fix: pixels whose separable blur value is too close to an integer
-    int fix_cap;
-    int* fix_count;                                   // [slot]
-    unsigned* fix_list;                               // [slot][fix_cap]: level<<28 | y<<14 | x
+    float blur_eps;                                   // JSFE_BLUR_EPS (6e-4); see DESIGN.md 4.2
+    int fix_items_total;                              // k_blur_fix threads (16 mask bytes each) over all levels
+    int fix_item_start[JSFE_MAXL + 1];
 };
 
 // TMA descriptors (cuTensorMapEncodeTiled, 3-D u8 tensors {pitch, h, slots}), passed as one __grid_constant__ parameter.
