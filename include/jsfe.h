@@ -172,6 +172,22 @@ int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_resul
 int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
                             float mb, float mbf, jsfe_host_results* out);
 
+/* ---- adjacent rows: stateless helpers of the tracking thread.  All pointers are DEVICE pointers,
+ * work is enqueued on `stream` and NOT synchronised (the compat shims synchronise, as the reference does).
+ * jsfe_project_points replaces orb_cuda::ORB_Search_by_projection_project_on_frame (include/cuda/orb_matcher.hpp:11-17),
+ * jsfe_hamming_pairs  replaces orb_cuda::ORB_compute_distances                     (include/cuda/orb_matcher.hpp:19-23),
+ * jsfe_in_frustum     replaces tracking_cuda::compute_isInFrustum_GPU              (include/cuda/tracking_gpu.hpp:13-28). */
+int jsfe_project_points(int n, const float* px, const float* py, const float* pz, const float* rcw9, const float* tcw3, float fx,
+                        float fy, float cx, float cy, float min_x, float max_x, float min_y, float max_y, float* u, float* v,
+                        float* invz, uint8_t* is_valid, void* stream);
+int jsfe_hamming_pairs(int n, const int32_t* idx_left, const int32_t* idx_right, const uint8_t* desc_left,
+                       const uint8_t* desc_right, int32_t* distance, void* stream);
+int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, const float* pnx, const float* pny, const float* pnz,
+                    const float* max_distance, const float* invariance_max_distance, const float* invariance_min_distance,
+                    const float* rcw9, const float* tcw3, const float* ow3, float fx, float fy, float cx, float cy, int min_x,
+                    int max_x, int min_y, int max_y, int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz,
+                    float* u, float* v, int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream);
+
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
 /* the 7x7-blurred level (descriptor input); zero outside [20,h-20)x[20,w-20) like the reference's image_gaussian_ */

@@ -825,6 +825,41 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
     return JSFE_OK;
 }
 
+int jsfe_project_points(int n, const float* px, const float* py, const float* pz, const float* rcw9, const float* tcw3, float fx,
+                        float fy, float cx, float cy, float min_x, float max_x, float min_y, float max_y, float* u, float* v,
+                        float* invz, uint8_t* is_valid, void* stream) {
+    if (n < 0 || (n && (!px || !py || !pz || !rcw9 || !tcw3 || !u || !v || !invz || !is_valid))) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n == 0) return JSFE_OK;
+    jsfe::k_project_points<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, px, py, pz, rcw9, tcw3, fx, fy, cx, cy, min_x, max_x,
+                                                                                 min_y, max_y, u, v, invz, is_valid);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
+int jsfe_hamming_pairs(int n, const int32_t* idx_left, const int32_t* idx_right, const uint8_t* desc_left,
+                       const uint8_t* desc_right, int32_t* distance, void* stream) {
+    if (n < 0 || (n && (!idx_left || !idx_right || !desc_left || !desc_right || !distance))) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n == 0) return JSFE_OK;
+    jsfe::k_hamming_pairs<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, idx_left, idx_right, desc_left, desc_right, distance);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
+int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, const float* pnx, const float* pny, const float* pnz,
+                    const float* max_distance, const float* invariance_max_distance, const float* invariance_min_distance,
+                    const float* rcw9, const float* tcw3, const float* ow3, float fx, float fy, float cx, float cy, int min_x,
+                    int max_x, int min_y, int max_y, int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz,
+                    float* u, float* v, int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream) {
+    if (n < 0) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n == 0) return JSFE_OK;
+    jsfe::k_in_frustum<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, px, py, pz, pnx, pny, pnz, max_distance, invariance_max_distance,
+                                                                            invariance_min_distance, rcw9, tcw3, ow3, fx, fy, cx, cy, min_x, max_x,
+                                                                            min_y, max_y, n_scale_levels, log_scale_factor, view_cos_angle, invz, u, v,
+                                                                            predicted_level, view_cos, is_infrustum);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst) {
     int rc = check_slots(h, slot, 1);
     if (rc) return rc;

@@ -193,23 +193,27 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     __syncthreads();                      // also makes the mbarrier init visible to every thread
     if (p.use_tma) mbar_wait(&s_bar, 0);  // TMA bytes have landed
 
-    // ---- phase A: compass pre-test, 4 pixels per thread; thread = (column group g, row lane rl)
+    // ---- phase A: compass pre-test, 8 pixels (two 32-bit words) per thread and iteration;
+    //      thread = (column pair g, row lane rl); survivors go to the work list
     {
         const int cs0 = X0 - 1 - gx0;               // smem column of score column 0
-        const int g0 = cs0 >> 2, ngx = ((cs0 + GW + 1) >> 2) - g0 + 1;
+        const int g0 = cs0 >> 3, ngx = ((cs0 + GW + 1) >> 3) - g0 + 1;   // 8-pixel column pairs covering the score columns
         int nrl = 256 / ngx;
-        if (nrl < 1) nrl = 1;                       // (ngx <= 50 by construction)
+        if (nrl < 1) nrl = 1;                       // (ngx <= 26 by construction)
         // score rows whose y lies in the interior [B, h-B): ry in [ry_lo, ry_hi)
         const int ry_lo = max(0, JSFE_B - (y0 - 1)), ry_hi = min(SR, lv.h - JSFE_B - (y0 - 1));
         const int niter = (ry_hi - ry_lo + nrl - 1) / nrl;   // warp-uniform trip count: the list append is warp-collective
         const int rl = tid / ngx, g = tid - rl * ngx;
-        const int c = (g0 + g) << 2, xb = gx0 + c;
+        const int c = (g0 + g) << 3, xb = gx0 + c;
         const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
-        // column validity mask of this thread's 4 pixels (MSB per byte), hoisted out of the row loop
-        unsigned vmc = 0;
+        // column validity masks of this thread's 2 x 4 pixels (MSB per byte), hoisted out of the row loop
+        unsigned vma = 0, vmb = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) vmc |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
-        if (rl >= nrl) vmc = 0;
+        for (int k = 0; k < 4; ++k) {
+            vma |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
+            vmb |= (unsigned)(xb + 4 + k >= xlo && xb + 4 + k <= xhi) << (8 * k + 7);
+        }
+        if (rl >= nrl) { vma = 0; vmb = 0; }
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
         const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
         const int mode = p.compass_mode;
@@ -220,57 +224,69 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         int idx0 = ry * SW + (c - cs0);
         const int rstep = nrl * PW, istep = nrl * SW;
         const size_t mstep = (size_t)nrl * lv.pitch;
+        // one 4-pixel group: v = centre pixels, P0/P8 = rows +3/-3, P4/P12 = columns +3/-3
+        auto compass = [&](unsigned v, unsigned P0, unsigned P4, unsigned P8, unsigned P12) -> unsigned {
+            const unsigned nv7 = ~v & 0x7f7f7f7fu;
+            const unsigned df0 = msb_gt(__vabsdiffu4(P0, v), T4, nT7), gt0 = msb_gt(P0, v, nv7);
+            const unsigned df4 = msb_gt(__vabsdiffu4(P4, v), T4, nT7), gt4 = msb_gt(P4, v, nv7);
+            const unsigned df8 = msb_gt(__vabsdiffu4(P8, v), T4, nT7), gt8 = msb_gt(P8, v, nv7);
+            const unsigned df12 = msb_gt(__vabsdiffu4(P12, v), T4, nT7), gt12 = msb_gt(P12, v, nv7);
+            // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
+            const unsigned keep = (df4 | df12) & (df0 | df8);
+            unsigned cond;
+            if (mode == 2) {         // an arc of >= 8 covers two ADJACENT compass points: one of {0,8} and one of {4,12}
+                cond = (((df0 & gt0) | (df8 & gt8)) & ((df4 & gt4) | (df12 & gt12))) |
+                       (((df0 & ~gt0) | (df8 & ~gt8)) & ((df4 & ~gt4) | (df12 & ~gt12)));
+            } else if (mode == 3) {  // three adjacent compass points
+                const unsigned b0 = df0 & gt0, b4 = df4 & gt4, b8 = df8 & gt8, b12 = df12 & gt12;
+                const unsigned k0 = df0 & ~gt0, k4 = df4 & ~gt4, k8 = df8 & ~gt8, k12 = df12 & ~gt12;
+                cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
+                       (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
+            } else if (mode == 1) {
+                cond = df0 | df4 | df8 | df12;
+            } else {
+                cond = 0xffffffffu;
+            }
+            return cond & keep & 0x80808080u;
+        };
         for (int it = 0; it < niter; ++it, ry += nrl, rp += rstep, idx0 += istep) {
-            unsigned pass = 0;
-            if (vmc && ry < ry_hi) {
+            unsigned pa = 0, pb = 0;
+            if ((vma | vmb) && ry < ry_hi) {
                 const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
-                const unsigned W1 = *reinterpret_cast<const unsigned*>(rp);
-                const unsigned W2 = *reinterpret_cast<const unsigned*>(rp + 4);
-                const unsigned P0 = *reinterpret_cast<const unsigned*>(rp + 3 * PW);   // ring 0  (0,+3)
-                const unsigned P8 = *reinterpret_cast<const unsigned*>(rp - 3 * PW);   // ring 8  (0,-3)
-                const unsigned P4 = __byte_perm(W1, W2, 0x6543);                       // ring 4  (+3,0)
-                const unsigned P12 = __byte_perm(W0, W1, 0x4321);                      // ring 12 (-3,0)
-                const unsigned v = W1, nv7 = ~v & 0x7f7f7f7fu;
-                const unsigned df0 = msb_gt(__vabsdiffu4(P0, v), T4, nT7), gt0 = msb_gt(P0, v, nv7);
-                const unsigned df4 = msb_gt(__vabsdiffu4(P4, v), T4, nT7), gt4 = msb_gt(P4, v, nv7);
-                const unsigned df8 = msb_gt(__vabsdiffu4(P8, v), T4, nT7), gt8 = msb_gt(P8, v, nv7);
-                const unsigned df12 = msb_gt(__vabsdiffu4(P12, v), T4, nT7), gt12 = msb_gt(P12, v, nv7);
-                // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
-                const unsigned keep = (df4 | df12) & (df0 | df8);
-                unsigned cond;
-                if (mode == 2) {         // an arc of >= 8 covers two ADJACENT compass points: one of {0,8} and one of {4,12}
-                    cond = (((df0 & gt0) | (df8 & gt8)) & ((df4 & gt4) | (df12 & gt12))) |
-                           (((df0 & ~gt0) | (df8 & ~gt8)) & ((df4 & ~gt4) | (df12 & ~gt12)));
-                } else if (mode == 3) {  // three adjacent compass points
-                    const unsigned b0 = df0 & gt0, b4 = df4 & gt4, b8 = df8 & gt8, b12 = df12 & gt12;
-                    const unsigned k0 = df0 & ~gt0, k4 = df4 & ~gt4, k8 = df8 & ~gt8, k12 = df12 & ~gt12;
-                    cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
-                           (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
-                } else if (mode == 1) {
-                    cond = df0 | df4 | df8 | df12;
-                } else {
-                    cond = 0xffffffffu;
+                const uint2 W12 = *reinterpret_cast<const uint2*>(rp);          // c is a multiple of 8
+                const unsigned W3 = *reinterpret_cast<const unsigned*>(rp + 8);
+                const uint2 D = *reinterpret_cast<const uint2*>(rp + 3 * PW);    // ring 0  (0,+3)
+                const uint2 U = *reinterpret_cast<const uint2*>(rp - 3 * PW);    // ring 8  (0,-3)
+                pa = compass(W12.x, D.x, __byte_perm(W12.x, W12.y, 0x6543), U.x, __byte_perm(W0, W12.x, 0x4321)) & vma;
+                pb = compass(W12.y, D.y, __byte_perm(W12.y, W3, 0x6543), U.y, __byte_perm(W12.x, W12.y, 0x4321)) & vmb;
+                if (mp != nullptr) {
+                    const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mp));
+                    pa &= msb_gt(mw.x, 0u, 0x7f7f7f7fu);
+                    pb &= msb_gt(mw.y, 0u, 0x7f7f7f7fu);
                 }
-                pass = cond & keep & vmc;
-                if (mp != nullptr) pass &= msb_gt(__ldg(reinterpret_cast<const unsigned*>(mp)), 0u, 0x7f7f7f7fu);
             }
             if (mp != nullptr) mp += mstep;
-            // append survivors to the work list: exclusive prefix of the per-lane count (0..4) from 3 ballots
-            const unsigned cnt = (((pass >> 7) & 0x01010101u) * 0x01010101u) >> 24;
+            // append survivors to the work list: exclusive prefix of the per-lane count (0..8) from 4 ballots
+            const unsigned cnt = (((pa >> 7) + (pb >> 7)) * 0x01010101u) >> 24;
             const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u);
             const unsigned c1 = __ballot_sync(0xffffffffu, cnt & 2u);
             const unsigned c2 = __ballot_sync(0xffffffffu, cnt & 4u);
-            if (c0 | c1 | c2) {
-                const int pre = __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
+            const unsigned c3 = __ballot_sync(0xffffffffu, cnt & 8u);
+            if (c0 | c1 | c2 | c3) {
+                const int pre = __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt) + 8 * __popc(c3 & lt);
                 int base = pre + (int)cnt;                 // lane 31 holds the warp total
                 base = __shfl_sync(0xffffffffu, base, 31);
                 if (lane == 0) base = atomicAdd(&s_ncand, base);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 uint16_t* o = cand + base + pre;
-                if (pass & 0x00000080u) *o++ = (uint16_t)idx0;
-                if (pass & 0x00008000u) *o++ = (uint16_t)(idx0 + 1);
-                if (pass & 0x00800000u) *o++ = (uint16_t)(idx0 + 2);
-                if (pass & 0x80000000u) *o = (uint16_t)(idx0 + 3);
+                if (pa & 0x00000080u) *o++ = (uint16_t)idx0;
+                if (pa & 0x00008000u) *o++ = (uint16_t)(idx0 + 1);
+                if (pa & 0x00800000u) *o++ = (uint16_t)(idx0 + 2);
+                if (pa & 0x80000000u) *o++ = (uint16_t)(idx0 + 3);
+                if (pb & 0x00000080u) *o++ = (uint16_t)(idx0 + 4);
+                if (pb & 0x00008000u) *o++ = (uint16_t)(idx0 + 5);
+                if (pb & 0x00800000u) *o++ = (uint16_t)(idx0 + 6);
+                if (pb & 0x80000000u) *o = (uint16_t)(idx0 + 7);
             }
         }
     }
@@ -1024,6 +1040,90 @@ __global__ void k_pack(const __grid_constant__ Params p, int slot, int n, int* d
     }
     if (i < 8 * n && dst_desc)
         reinterpret_cast<uint32_t*>(dst_desc)[i] = reinterpret_cast<const uint32_t*>(p.desc + (size_t)slot * p.cap * 32)[i];
+}
+
+// =================================================================================================
+// Adjacent rows: the three helper kernels the tracking thread calls.  Straight SoA kernels, stream
+// ordered; float associations pinned with intrinsics to what nvcc emits for the reference (see oracle).
+//   k_project_points  replaces ORB_Search_by_projection_project_on_GPU (src/cuda/orb_matcher.cu:17-64)
+//   k_hamming_pairs   replaces ORB_compute_descriptor_Distance_GPU     (src/cuda/orb_matcher.cu:95-118)
+//   k_in_frustum      replaces isInFrustum_GPU                         (src/cuda/tracking_isinfrustum.cu:19-107)
+// =================================================================================================
+__device__ __forceinline__ float dot3_plus(float a, float ra, float b, float rb, float c, float rc, float t) {
+    return __fadd_rn(__fmaf_rn(c, rc, __fmaf_rn(b, rb, __fmul_rn(a, ra))), t);
+}
+
+__global__ void __launch_bounds__(256) k_project_points(int n, const float* __restrict__ px, const float* __restrict__ py,
+                                                        const float* __restrict__ pz, const float* __restrict__ Rcw,
+                                                        const float* __restrict__ tcw, float fx, float fy, float cx, float cy,
+                                                        float min_x, float max_x, float min_y, float max_y, float* __restrict__ u,
+                                                        float* __restrict__ v, float* __restrict__ invz, uint8_t* __restrict__ is_valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = px[i], y = py[i], z = pz[i];
+    const float X = dot3_plus(x, __ldg(Rcw + 0), y, __ldg(Rcw + 1), z, __ldg(Rcw + 2), __ldg(tcw + 0));
+    const float Y = dot3_plus(x, __ldg(Rcw + 3), y, __ldg(Rcw + 4), z, __ldg(Rcw + 5), __ldg(tcw + 1));
+    const float Z = dot3_plus(x, __ldg(Rcw + 6), y, __ldg(Rcw + 7), z, __ldg(Rcw + 8), __ldg(tcw + 2));
+    float iz = -1.0f, uu = -1.0f, vv = -1.0f;
+    uint8_t ok = 0;
+    if (Z > 0.0f) {
+        iz = __frcp_rn(Z);
+        uu = __fmaf_rn(__fmul_rn(X, fx), iz, cx);
+        vv = __fmaf_rn(__fmul_rn(Y, fy), iz, cy);
+        if (!(uu < min_x || uu > max_x || vv < min_y || vv > max_y)) ok = 1;
+    }
+    u[i] = uu; v[i] = vv; invz[i] = iz; is_valid[i] = ok;
+}
+
+__global__ void __launch_bounds__(256) k_hamming_pairs(int n, const int* __restrict__ idx_l, const int* __restrict__ idx_r,
+                                                       const uint8_t* __restrict__ desc_l, const uint8_t* __restrict__ desc_r,
+                                                       int* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* a = reinterpret_cast<const uint4*>(desc_l + (size_t)idx_l[i] * 32);
+    const uint4* b = reinterpret_cast<const uint4*>(desc_r + (size_t)idx_r[i] * 32);
+    const uint4 a0 = __ldg(a), a1 = __ldg(a + 1), b0 = __ldg(b), b1 = __ldg(b + 1);
+    dist[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(256) k_in_frustum(int n, const float* __restrict__ px, const float* __restrict__ py,
+                                                    const float* __restrict__ pz, const float* __restrict__ pnx,
+                                                    const float* __restrict__ pny, const float* __restrict__ pnz,
+                                                    const float* __restrict__ max_distance, const float* __restrict__ inv_max,
+                                                    const float* __restrict__ inv_min, const float* __restrict__ Rcw,
+                                                    const float* __restrict__ tcw, const float* __restrict__ Ow, float fx, float fy,
+                                                    float cx, float cy, int min_x, int max_x, int min_y, int max_y, int n_levels,
+                                                    float log_sf, float view_cos_angle, float* __restrict__ invz, float* __restrict__ u,
+                                                    float* __restrict__ v, int* __restrict__ level, float* __restrict__ view_cos,
+                                                    uint8_t* __restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t ok = 0;
+    const float x = px[i], y = py[i], z = pz[i];
+    const float X = dot3_plus(x, __ldg(Rcw + 0), y, __ldg(Rcw + 1), z, __ldg(Rcw + 2), __ldg(tcw + 0));
+    const float Y = dot3_plus(x, __ldg(Rcw + 3), y, __ldg(Rcw + 4), z, __ldg(Rcw + 5), __ldg(tcw + 1));
+    const float Z = dot3_plus(x, __ldg(Rcw + 6), y, __ldg(Rcw + 7), z, __ldg(Rcw + 8), __ldg(tcw + 2));
+    if (Z > 0.0f) {
+        const float iz = __frcp_rn(Z);
+        const float uu = __fmaf_rn(__fmul_rn(X, fx), iz, cx), vv = __fmaf_rn(__fmul_rn(Y, fy), iz, cy);
+        if (!(uu < (float)min_x || uu > (float)max_x || vv < (float)min_y || vv > (float)max_y)) {
+            const float ox = __fsub_rn(x, __ldg(Ow + 0)), oy = __fsub_rn(y, __ldg(Ow + 1)), oz = __fsub_rn(z, __ldg(Ow + 2));
+            // association measured on the reference's sm_100a build: the SECOND product is the plain FMUL (tests/test_helpers.py)
+            const float dist = __fsqrt_rn(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));
+            if (!(dist < inv_min[i] || dist > inv_max[i])) {
+                const float vc = __fdiv_rn(__fmaf_rn(oz, pnz[i], __fmaf_rn(ox, pnx[i], __fmul_rn(oy, pny[i]))), dist);
+                if (!(vc < view_cos_angle)) {
+                    const float ratio = __fdiv_rn(max_distance[i], dist);
+                    int ns = (int)ceilf(__fdiv_rn(logf(ratio), log_sf));
+                    if (ns < 0) ns = 0; else if (ns >= n_levels) ns = n_levels - 1;
+                    u[i] = uu; v[i] = vv; invz[i] = iz; level[i] = ns; view_cos[i] = vc;
+                    ok = 1;
+                }
+            }
+        }
+    }
+    in[i] = ok;
 }
 
 }  // namespace jsfe

@@ -80,6 +80,10 @@ def lib():
         L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
         L.jsfe_process_host_pairs.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(HostResults)]
+        f = C.c_float
+        L.jsfe_project_points.argtypes = [C.c_int] + [vp] * 5 + [f] * 8 + [vp] * 4 + [vp]
+        L.jsfe_hamming_pairs.argtypes = [C.c_int] + [vp] * 5 + [vp]
+        L.jsfe_in_frustum.argtypes = [C.c_int] + [vp] * 12 + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
         L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_level_blur.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -311,3 +315,45 @@ class StereoORB:
         ur, dp, bi, bd = self.fe.get_stereo(0)
         return {"kps_l": kl, "desc_l": dl, "kps_r": kr, "desc_r": dr, "u_right": ur, "depth": dp, "best_idx_r": bi,
                 "best_dist": bd}
+
+
+# ---- adjacent rows: stateless helpers on DEVICE arrays (torch CUDA tensors are the plumbing here) ----------
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def project_points(P, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_y, max_y, stream=None):
+    """Mirror of orb_cuda::ORB_Search_by_projection_project_on_frame (include/cuda/orb_matcher.hpp:11-17).
+    P: [3, n] f32 CUDA tensor (Px|Py|Pz planes), Rcw [9], tcw [3] f32 CUDA.  Returns (u, v, invz, is_valid) CUDA tensors."""
+    import torch
+    n = P.shape[1]
+    u, v, iz = (torch.empty(n, dtype=torch.float32, device=P.device) for _ in range(3))
+    ok = torch.empty(n, dtype=torch.uint8, device=P.device)
+    _check(lib().jsfe_project_points(n, _ptr(P[0]), _ptr(P[1]), _ptr(P[2]), _ptr(Rcw), _ptr(tcw), fx, fy, cx, cy, min_x, max_x,
+                                     min_y, max_y, _ptr(u), _ptr(v), _ptr(iz), _ptr(ok), _stream_ptr(stream)))
+    return u, v, iz, ok
+
+
+def hamming_pairs(idx_l, idx_r, desc_l, desc_r, stream=None):
+    """Mirror of orb_cuda::ORB_compute_distances (include/cuda/orb_matcher.hpp:19-23): int32 CUDA index tensors, u8 [N,32] descriptors."""
+    import torch
+    n = idx_l.shape[0]
+    d = torch.empty(n, dtype=torch.int32, device=idx_l.device)
+    _check(lib().jsfe_hamming_pairs(n, _ptr(idx_l), _ptr(idx_r), _ptr(desc_l), _ptr(desc_r), _ptr(d), _stream_ptr(stream)))
+    return d
+
+
+def in_frustum(P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels,
+               log_scale_factor, view_cos_angle, stream=None):
+    """Mirror of tracking_cuda::compute_isInFrustum_GPU (include/cuda/tracking_gpu.hpp:13-28).  Outputs other than the flag are
+    defined only where the flag is 1 (as in the reference); they are zero-initialised here."""
+    import torch
+    n = P.shape[1]
+    iz, u, v, vc = (torch.zeros(n, dtype=torch.float32, device=P.device) for _ in range(4))
+    lvl = torch.zeros(n, dtype=torch.int32, device=P.device)
+    ok = torch.empty(n, dtype=torch.uint8, device=P.device)
+    _check(lib().jsfe_in_frustum(n, _ptr(P[0]), _ptr(P[1]), _ptr(P[2]), _ptr(Pn[0]), _ptr(Pn[1]), _ptr(Pn[2]), _ptr(max_distance),
+                                 _ptr(inv_max), _ptr(inv_min), _ptr(Rcw), _ptr(tcw), _ptr(Ow), fx, fy, cx, cy, min_x, max_x, min_y,
+                                 max_y, n_levels, log_scale_factor, view_cos_angle, _ptr(iz), _ptr(u), _ptr(v), _ptr(lvl), _ptr(vc),
+                                 _ptr(ok), _stream_ptr(stream)))
+    return iz, u, v, lvl, vc, ok

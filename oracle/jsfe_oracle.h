@@ -23,8 +23,10 @@
  * Parity pin: the reference ships NO tests, fixtures or golden vectors for this
  * path.  This oracle is pinned against the reference's own
  * src/cuda compiled unmodified for sm_100a (oracle/ref_build -> oracle/_ref)
- * and run on a B200; the resulting vectors are committed under tests/golden/.
- * Until tests/golden/ref_*.npz exist the status is "parity unpinned".
+ * and run on a B200; the resulting vectors are committed under tests/golden/ref_*.npz
+ * (tools/make_golden.py; report: tests/golden/pin_report_r1_run*.json -- every stage bit-identical).
+ * Status: PINNED for the extraction + stereo path.  The three adjacent helpers at the end of this file are
+ * checked against the reference kernels on the GPU box by tests/test_gpu_helpers.py (no committed fixture).
  */
 #ifndef JSFE_ORACLE_H
 #define JSFE_ORACLE_H
@@ -123,6 +125,24 @@ int orc_stereo_match(const orc_ctx* cl, const orc_ctx* cr, int th_high, int th_l
 int orc_stereo_pair(orc_ctx* cl, orc_ctx* cr, const uint8_t* img_l, const uint8_t* img_r,
                     float mb, float mbf, int32_t* kps_l, uint8_t* desc_l, int32_t* n_r_out,
                     int32_t* kps_r, uint8_t* desc_r, float* u_right, float* depth, int threads);
+
+/* ---- adjacent rows: helpers of ORBmatcher::SearchByProjection and Tracking::SearchLocalPoints ---- */
+float orc_logf(float x); /* libdevice logf transcription */
+/* src/cuda/orb_matcher.cu:17-64: Pc = R*Pw + t, pinhole projection, bounds check */
+void orc_project_points(int n, const float* px, const float* py, const float* pz, const float* rcw9, const float* tcw3,
+                        float fx, float fy, float cx, float cy, float min_x, float max_x, float min_y, float max_y,
+                        float* u, float* v, float* invz, uint8_t* is_valid);
+/* src/cuda/orb_matcher.cu:95-118: 256-bit Hamming distance of indexed descriptor pairs */
+void orc_hamming_pairs(int n, const int32_t* idx_l, const int32_t* idx_r, const uint8_t* desc_l, const uint8_t* desc_r,
+                       int32_t* dist);
+/* src/cuda/tracking_isinfrustum.cu:19-107: Frame::isInFrustum per map point.  Outputs other than is_infrustum are
+ * written only for points inside the frustum (as in the reference). */
+void orc_in_frustum(int n, const float* px, const float* py, const float* pz, const float* pnx, const float* pny,
+                    const float* pnz, const float* max_distance, const float* inv_max_distance,
+                    const float* inv_min_distance, const float* rcw9, const float* tcw3, const float* ow3, float fx,
+                    float fy, float cx, float cy, int min_x, int max_x, int min_y, int max_y, int n_scale_levels,
+                    float log_scale_factor, float view_cos_angle, float* invz, float* u, float* v,
+                    int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum);
 
 #ifdef __cplusplus
 }

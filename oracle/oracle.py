@@ -76,6 +76,12 @@ def lib():
         L.orc_stereo_pair.argtypes = [vp, vp, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int]
+        f, vpp, ci = C.c_float, C.c_void_p, C.c_int
+        L.orc_logf.restype = f
+        L.orc_logf.argtypes = [f]
+        L.orc_project_points.argtypes = [ci] + [vpp] * 5 + [f] * 8 + [vpp] * 4
+        L.orc_hamming_pairs.argtypes = [ci] + [vpp] * 5
+        L.orc_in_frustum.argtypes = [ci] + [vpp] * 12 + [f] * 4 + [ci] * 5 + [f] * 2 + [vpp] * 6
         _lib = L
     return _lib
 
@@ -179,3 +185,36 @@ def stereo_match(left: Oracle, right: Oracle, kps_l, desc_l, kps_r, desc_r, mb, 
                            nr, kr.ctypes.data, dr.ctypes.data, ur.ctypes.data, dp.ctypes.data,
                            bi.ctypes.data, bd.ctypes.data)
     return ur[:nl], dp[:nl], bi[:nl], bd[:nl]
+
+
+def project_points(P, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_y, max_y):
+    P = np.ascontiguousarray(P, np.float32); Rcw = np.ascontiguousarray(Rcw, np.float32); tcw = np.ascontiguousarray(tcw, np.float32)
+    n = P.shape[1]
+    u, v, iz = (np.zeros(n, np.float32) for _ in range(3))
+    ok = np.zeros(n, np.uint8)
+    lib().orc_project_points(n, P[0].ctypes.data, P[1].ctypes.data, P[2].ctypes.data, Rcw.ctypes.data, tcw.ctypes.data, fx, fy, cx, cy,
+                             min_x, max_x, min_y, max_y, u.ctypes.data, v.ctypes.data, iz.ctypes.data, ok.ctypes.data)
+    return u, v, iz, ok
+
+
+def hamming_pairs(idx_l, idx_r, desc_l, desc_r):
+    il = np.ascontiguousarray(idx_l, np.int32); ir = np.ascontiguousarray(idx_r, np.int32)
+    dl = np.ascontiguousarray(desc_l, np.uint8); dr = np.ascontiguousarray(desc_r, np.uint8)
+    d = np.zeros(len(il), np.int32)
+    lib().orc_hamming_pairs(len(il), il.ctypes.data, ir.ctypes.data, dl.ctypes.data, dr.ctypes.data, d.ctypes.data)
+    return d
+
+
+def in_frustum(P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels,
+               log_scale_factor, view_cos_angle):
+    a = lambda x: np.ascontiguousarray(x, np.float32)
+    P, Pn, md, ima, imi, Rcw, tcw, Ow = map(a, (P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow))
+    n = P.shape[1]
+    iz, u, v, vc = (np.zeros(n, np.float32) for _ in range(4))
+    lvl = np.zeros(n, np.int32)
+    ok = np.zeros(n, np.uint8)
+    lib().orc_in_frustum(n, P[0].ctypes.data, P[1].ctypes.data, P[2].ctypes.data, Pn[0].ctypes.data, Pn[1].ctypes.data,
+                         Pn[2].ctypes.data, md.ctypes.data, ima.ctypes.data, imi.ctypes.data, Rcw.ctypes.data, tcw.ctypes.data,
+                         Ow.ctypes.data, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels, log_scale_factor, view_cos_angle,
+                         iz.ctypes.data, u.ctypes.data, v.ctypes.data, lvl.ctypes.data, vc.ctypes.data, ok.ctypes.data)
+    return iz, u, v, lvl, vc, ok

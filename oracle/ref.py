@@ -39,6 +39,10 @@ def lib():
         L.jsref_stereo_match.argtypes = [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp]
         L.jsref_time_pairs.restype = C.c_double
         L.jsref_time_pairs.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, C.c_int]
+        f, ci = C.c_float, C.c_int
+        L.jsref_project_points.argtypes = [ci] + [vp] * 5 + [f] * 8 + [vp] * 4
+        L.jsref_hamming_pairs.argtypes = [ci] + [vp] * 5
+        L.jsref_in_frustum.argtypes = [ci] + [vp] * 12 + [f] * 4 + [ci] * 5 + [f] * 2 + [vp] * 6
         _lib = L
     return _lib
 

@@ -5,6 +5,8 @@
 // way Frame::Frame / Frame::ComputeStereoMatches do (src/Frame.cpp:80-250,780-803) and exposes
 // intermediate buffers so the CPU oracle and the new CUDA path can be pinned against them.
 #include <cuda/orb_gpu.hpp>
+#include <cuda/orb_matcher.hpp>
+#include <cuda/tracking_gpu.hpp>
 
 #include <chrono>
 #include <cstdint>
@@ -174,6 +176,21 @@ double jsref_time_pairs(void* hl, void* hr, const uint8_t* img_l, const uint8_t*
     }
     cudaDeviceSynchronize();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- adjacent helpers: thin pass-throughs to the reference's own functions (device pointers) ----
+void jsref_project_points(int n, float* px, float* py, float* pz, float* R, float* t, float fx, float fy, float cx, float cy,
+                          float minx, float maxx, float miny, float maxy, float* u, float* v, float* invz, unsigned char* ok) {
+    orb_cuda::ORB_Search_by_projection_project_on_frame(n, px, py, pz, R, t, fx, fy, cx, cy, minx, maxx, miny, maxy, u, v, invz, ok);
+}
+void jsref_hamming_pairs(int n, int* il, int* ir, unsigned char* dl, unsigned char* dr, int* dist) {
+    orb_cuda::ORB_compute_distances(n, il, ir, dl, dr, dist);
+}
+void jsref_in_frustum(int n, float* px, float* py, float* pz, float* pnx, float* pny, float* pnz, float* md, float* imax, float* imin,
+                      float* R, float* t, float* ow, float fx, float fy, float cx, float cy, int minx, int maxx, int miny, int maxy,
+                      int nlev, float logsf, float vca, float* invz, float* u, float* v, int* lvl, float* vc, unsigned char* in) {
+    tracking_cuda::compute_isInFrustum_GPU(n, px, py, pz, pnx, pny, pnz, md, imax, imin, R, t, ow, fx, fy, cx, cy, minx, maxx, miny, maxy,
+                                           nlev, logsf, vca, invz, u, v, lvl, vc, in);
 }
 
 }  // extern "C"
