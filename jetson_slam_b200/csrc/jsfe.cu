@@ -93,6 +93,10 @@ struct jsfe_handle {
     std::vector<cudaEvent_t> event_pool;
     // end-to-end pipeline (jsfe_process_host_pairs): unpitched H2D staging + three streams
     int chunk_images = 0;
+    // k_blur (FP32-pipe bound) runs beside k_fast_cells (integer-ALU bound) on an auxiliary stream
+    cudaStream_t st_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap_blur = 1;
     uint8_t* d_stage = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;
@@ -442,6 +446,11 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         h->chunk_images = 0;
         if (const char* e = getenv("JSFE_CHUNK_IMAGES")) h->chunk_images = atoi(e);
     }
+    if (const char* e = getenv("JSFE_NO_OVERLAP")) h->overlap_blur = atoi(e) ? 0 : 1;
+    if (cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(JSFE_ERR_CUDA, "stream/event creation failed"));
     CU(cudaDeviceSynchronize());
     *out = h;
     return JSFE_OK;
@@ -456,6 +465,9 @@ int jsfe_destroy(jsfe_handle* h) {
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    if (h->st_aux) cudaStreamDestroy(h->st_aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
     if (h->st_comp) cudaStreamDestroy(h->st_comp);
     if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
@@ -535,6 +547,13 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
         jsfe::k_pyramid<<<dim3(P.pyr_blocks_total, n), 256, 0, st>>>(P, first_slot);
         if ((rc = post_launch(h, "k_pyramid"))) return rc;
     }
+    // fork: the blur of every level depends only on the pyramid, not on FAST; when profiling per kernel, stay serial
+    const bool overlap = h->overlap_blur && !h->profiling && P.blur_items_total > 0;
+    cudaStream_t sb = overlap ? h->st_aux : st;
+    if (overlap) {
+        CU(cudaEventRecord(h->ev_fork, st));
+        CU(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+    }
     {
         StageTimer t(h, st, 1);
         jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, h->tma, first_slot);
@@ -542,15 +561,16 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     if ((rc = post_launch(h, "k_fast_cells"))) return rc;
     if (P.blur_items_total > 0) {
         {
-            StageTimer t(h, st, 7);
-            jsfe::k_blur<<<dim3((P.blur_items_total + 255) / 256, n), 256, 0, st>>>(P, first_slot);
+            StageTimer t(h, sb, 7);
+            jsfe::k_blur<<<dim3((P.blur_items_total + 255) / 256, n), 256, 0, sb>>>(P, first_slot);
         }
         if ((rc = post_launch(h, "k_blur"))) return rc;
         {
-            StageTimer t(h, st, 8);
-            jsfe::k_blur_fix<<<dim3((P.fix_items_total + 1023) / 1024, n), 256, 0, st>>>(P, first_slot);
+            StageTimer t(h, sb, 8);
+            jsfe::k_blur_fix<<<dim3((P.fix_items_total + 1023) / 1024, n), 256, 0, sb>>>(P, first_slot);
         }
         if ((rc = post_launch(h, "k_blur_fix"))) return rc;
+        if (overlap) CU(cudaEventRecord(h->ev_join, sb));
     }
     if (h->cfg.apply_nms_ms && P.L > 1) {  // orb_gpu.cpp:665-712
         {
@@ -565,6 +585,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
         jsfe::k_compact<<<n, 1024, 0, st>>>(P, first_slot);
     }
     if ((rc = post_launch(h, "k_compact"))) return rc;
+    if (overlap) CU(cudaStreamWaitEvent(st, h->ev_join, 0));   // join: the descriptor samples the blurred levels
     {
         StageTimer t(h, st, 3);
         jsfe::k_orient_desc<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, h->tma, first_slot);
