@@ -224,7 +224,9 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         int T = (g.tile_h - 1) / n_loc + 1;
         if (T * 128 > 1024) T = 1024 / 128;
         g.T = T;
-        g.cells_per_block = std::max(1, std::min(g.n_tile_w, 192 / g.tile_w));
+        int fast_width = 192;   // pixels of cell group per k_fast_cells block (s_best/s_colkey hold 192 columns)
+        if (const char* e = getenv("JSFE_FAST_WIDTH")) fast_width = std::max(16, std::min(192, atoi(e)));
+        g.cells_per_block = std::max(1, std::min(g.n_tile_w, fast_width / g.tile_w));
         g.blocks_per_row = (g.n_tile_w + g.cells_per_block - 1) / g.cells_per_block;
         g.block_offset = items;
         items += g.blocks_per_row * g.n_tile_h;
@@ -232,7 +234,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const size_t pw = align_up(gw + 8 + 15, 16), pr = g.tile_h + 8;   // covers X0+GW+4-gx0 with gx0 = floor16(X0-4)
         g.tile_pw = (int)pw;
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
-        smem_max = std::max(smem_max, pr * pw + 2 * (size_t)(g.tile_h + 2) * sw * 2 + 16);  // pixels + scores + work list
+        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 9 / 4 + 64);  // pixels + scores + work list + positives (1/4)
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
         if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 31) / 32);
         if (g.w >= 16384 || g.h >= 16384) { delete h; return fail(JSFE_ERR_INVALID, "images larger than 16383 pixels are not supported"); }

@@ -123,11 +123,9 @@ __device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b, unsigned nb7)
     return (a & ~b) | (~(a ^ b) & t);
 }
 
-// scalar reference form, kept for documentation and used by nothing on the hot path
-__device__ __forceinline__ unsigned nibble_of_msbs(unsigned flags) {
-    // gathers bit7 of each byte into bits 0..3 (byte k -> bit k): ((x>>7)&0x01010101) * 0x01020408 >> 24
-    return (((flags >> 7) & 0x01010101u) * 0x01020408u) >> 24;
-}
+// gathers bit 7 of the 4 bytes of `msbs` (already masked with 0x80808080) into bits 28..31 (byte k -> bit 28+k):
+// the multiplier 2^21 + 2^14 + 2^7 + 1 moves bit 8k+7 to 28+k and no two partial products collide, so there are no carries
+__device__ __forceinline__ unsigned top_nibble_of_msbs(unsigned msbs) { return msbs * 0x00204081u; }
 
 __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -135,7 +133,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     __shared__ unsigned s_best[192];
     __shared__ uint16_t s_colkey[192];   // per owned column: (127 - priority rank) << 8 | cell index
     __shared__ uint16_t s_rowkey[256];   // per owned row dy: (7 - dy % T) << 8 | (255 - dy)
-    __shared__ int s_ncand;
+    __shared__ int s_ncand, s_npos;
     int l = 0;
     while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l + 1].block_offset) ++l;
     const LevelGeom& lv = p.lv[l];
@@ -153,6 +151,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     uint8_t* pix = smem;
     uint16_t* sc = reinterpret_cast<uint16_t*>(smem + (size_t)PR * PW);
     uint16_t* cand = sc + (size_t)SR * SW;
+    uint16_t* pos = cand + (size_t)SR * SW;          // positives list (capacity = a quarter of the work list)
+    const int pos_cap = (SR * SW) >> 2;
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         if (tid < lv.tile_h) s_rowkey[tid] = (uint16_t)(((7u - (unsigned)(tid % lv.T)) << 8) | (255u - (unsigned)tid));
         if (tid == 0) {
             s_ncand = 0;
+            s_npos = 0;
         }
     }
     __syncthreads();                      // also makes the mbarrier init visible to every thread
@@ -300,8 +301,12 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
         const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
         const int cs0 = X0 - 1 - gx0;
-        for (int i = tid; i < ncand; i += 256) {
-            const int idx = cand[i];
+        const int nit = (ncand + 255) >> 8;       // warp-uniform trip count: the positives append is warp-collective
+        for (int it = 0, i = tid; it < nit; ++it, i += 256) {
+            unsigned score = 0;
+            int idx = 0;
+          if (i < ncand) {
+            idx = cand[i];
             const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
             const int rx = idx - ry * SW;
             const uint8_t* c = pix + (ry + 3) * PW + (cs0 + rx);
@@ -317,13 +322,25 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 const unsigned R = q == 0 ? R0 : q == 1 ? R1 : q == 2 ? R2 : R3;
                 sad = __vsadu4(R, V) + sad;
                 const unsigned df = msb_gt(__vabsdiffu4(R, V), T4, nT7), gt = msb_gt(R, V, nV7);
-                bright |= nibble_of_msbs(df & gt) << (4 * q);
-                dark |= nibble_of_msbs(df & ~gt) << (4 * q);
+                // ring points 4q..4q+3 enter at bits 28..31; after 4 words the 16 flags sit in bits 16..31, ring 0 lowest
+                bright = (bright >> 4) | (top_nibble_of_msbs(df & gt & 0x80808080u) & 0xF0000000u);
+                dark = (dark >> 4) | (top_nibble_of_msbs(df & ~gt & 0x80808080u) & 0xF0000000u);
             }
-            bright &= 0xFFFFu;
-            dark &= 0xFFFFu;
+            bright >>= 16;
+            dark >>= 16;
             const unsigned hit = ((__ldg(lut + (bright >> 5)) >> (bright & 31)) | (__ldg(lut + (dark >> 5)) >> (dark & 31))) & 1u;
-            sc[idx] = (uint16_t)(hit ? sad : 0u);
+            score = hit ? sad : 0u;
+            sc[idx] = (uint16_t)score;
+          }
+            // positives (about 40 % of the candidates) go to a second, smaller list so that phase C runs dense
+            const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);
+            if (pb) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_npos, __popc(pb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int o = base + __popc(pb & ((1u << lane) - 1u));
+                if (score != 0u && o < pos_cap) pos[o] = (uint16_t)idx;
+            }
         }
     }
     __syncthreads();
@@ -332,8 +349,12 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     {
         const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
         const int wv = min(GW, lv.w - X0);          // owned columns actually inside the image
-        for (int i = tid; i < ncand; i += 256) {
-            const int idx = cand[i];
+        const int npos = s_npos;
+        const bool dense = npos <= pos_cap;          // else: noise-like tile, walk the candidate list instead
+        const uint16_t* list = dense ? pos : cand;
+        const int nlist = dense ? npos : ncand;
+        for (int i = tid; i < nlist; i += 256) {
+            const int idx = list[i];
             const unsigned s = sc[idx];
             if (s) {
                 const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
@@ -512,24 +533,24 @@ __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ Params
         const int row = li / vpr, v = li - row * vpr;
         const uint4 m = __ldg(reinterpret_cast<const uint4*>(lv.amb + (size_t)slot * lv.amb_stride + (size_t)row * lv.amb_pitch) + v);
         if ((m.x | m.y | m.z | m.w) == 0u) continue;
-        const unsigned words[4] = {m.x, m.y, m.z, m.w};
+        // 16 mask bytes (low nibble = 4 pixels each) -> one 64-bit pixel mask; then visit only the set bits
+        auto squeeze = [](unsigned w) -> unsigned long long {
+            return (unsigned long long)((w & 0xFu) | ((w >> 4) & 0xF0u) | ((w >> 8) & 0xF00u) | ((w >> 12) & 0xF000u));
+        };
+        unsigned long long bits = squeeze(m.x) | (squeeze(m.y) << 16) | (squeeze(m.z) << 32) | (squeeze(m.w) << 48);
         const int y = JSFE_B + row;
-#pragma unroll 1
-        for (int i = 0; i < 16; ++i) {
-            const unsigned bits = (words[i >> 2] >> (8 * (i & 3))) & 0xFu;
-            if (!bits) continue;
-            const int xg = JSFE_B + ((v * 16 + i) << 2);
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const int x = xg + k;
-                if (!((bits >> k) & 1u) || x >= lv.w - JSFE_B) continue;
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < JSFE_FIX_LIST) {
-                    s_list[pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)x;
-                } else {
-                    const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
-                    lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
-                }
+        const int xbase = JSFE_B + (v << 6);
+        while (bits) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int x = xbase + b;
+            if (x >= lv.w - JSFE_B) break;            // pad columns of the last group (higher bits are further right)
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < JSFE_FIX_LIST) {
+                s_list[pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)x;
+            } else {
+                const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
+                lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
             }
         }
     }
