@@ -291,6 +291,12 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             ++v0;
         }
     }
+    P.vmax_packed = 0;
+    for (int au = 0; au <= 15; ++au) {
+        int vmax = 0;
+        for (int v = 0; v <= 15; ++v) if (au <= T->umax[v]) vmax = v;
+        P.vmax_packed |= (unsigned long long)vmax << (4 * au);
+    }
     {  // 7x7 sigma=10 weights (orb_gpu.cpp:196-218): double exp of a float argument, float sum, float divide
         const float sigma2 = 10.0f * 10.0f;
         float sum = 0;
@@ -336,6 +342,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     for (int i = 0; i < 512; ++i) {  // orb_bitpattern.cpp:266-273
         T->pat_x[i] = (int8_t)kPattern[2 * i];
         T->pat_y[i] = (int8_t)kPattern[2 * i + 1];
+        T->pat_f[(i & 15) * 32 + (i >> 4)] = make_float2((float)T->pat_x[i], (float)T->pat_y[i]);  // [sample j][byte b]: bank-conflict-free per lane
     }
     for (int i = 0; i < P.L; ++i) column_rank(P.lv[i].tile_w, T->col_rank[i], T->col_by_rank[i]);
 
@@ -590,7 +597,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     if (overlap) CU(cudaStreamWaitEvent(st, h->ev_join, 0));   // join: the descriptor samples the blurred levels
     {
         StageTimer t(h, st, 3);
-        jsfe::k_orient_desc<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, h->tma, first_slot);
+        jsfe::k_orient_desc<<<dim3((P.cap + 8 * JSFE_KP_PER_WARP - 1) / (8 * JSFE_KP_PER_WARP), n), 256, 0, st>>>(P, h->tma, first_slot);
     }
     if ((rc = post_launch(h, "k_orient_desc"))) return rc;
     return JSFE_OK;

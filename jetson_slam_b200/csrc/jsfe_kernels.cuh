@@ -773,104 +773,123 @@ __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params
 #define JSFE_WIN_SLOT 2432                                   // 2368 rounded up to 128
 #define JSFE_WARP_SMEM (JSFE_WIN_SLOT + 1536)                // + disc (1488 rounded up to 128)
 
+#define JSFE_KP_PER_WARP 1   // keypoints a warp processes one after the other (amortises the pattern staging)
+
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
     __shared__ __align__(128) uint8_t s_buf[8][JSFE_WARP_SMEM];
     __shared__ __align__(8) uint64_t s_bar[8];
-    __shared__ int8_t s_px[512], s_py[512];
+    __shared__ float2 s_pat[512];                    // rBRIEF sample offsets as floats (x, y)
     const int slot = slot0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = p.n_kp[slot];
-    if ((int)blockIdx.x * 8 >= n) return;
-    const int o = blockIdx.x * 8 + warp;
-    const size_t so = (size_t)slot * p.cap + min(o, n - 1);
-    const int x = p.kp_x[so], y = p.kp_y[so], l = p.kp_l[so], score = p.kp_s[so];
-    const LevelGeom& lv = p.lv[l];
+    const int o0 = (blockIdx.x * 8 + warp) * JSFE_KP_PER_WARP;    // this warp's keypoints: o0 .. o0+3
+    if ((int)blockIdx.x * 8 * JSFE_KP_PER_WARP >= n) return;
     uint8_t* win = s_buf[warp];                     // blurred window rows y-18..y+18, columns from wx0 (pitch 64)
     uint8_t* disc = s_buf[warp] + JSFE_WIN_SLOT;    // level image rows y-15..y+15, columns from dx0 (pitch 48)
-    const int wx0 = (x - JSFE_DP_R) & ~15, dx0 = (x - 15) & ~15;   // x >= 20, so both are >= 0
-    if (p.use_tma) {
-        // two TMA box loads per keypoint, issued by one lane; rows/columns outside the image arrive as 0
-        if (lane == 0 && o < n) {
-            mbar_init(&s_bar[warp], 1);
-            mbar_expect_tx(&s_bar[warp], JSFE_WIN_BYTES + JSFE_DISC_BYTES);
-            tma_load_3d(win, &tm.win[l], &s_bar[warp], wx0, y - JSFE_DP_R, slot);
-            tma_load_3d(disc, &tm.disc[l], &s_bar[warp], dx0, y - 15, slot);
+    uint64_t* bar = &s_bar[warp];
+
+    // keypoint record of iteration k (lane-uniform); loads for the next keypoint are issued as soon as the buffers are free
+    auto issue = [&](int o, int& x, int& y, int& l, int& score) {
+        const size_t so = (size_t)slot * p.cap + o;
+        x = p.kp_x[so]; y = p.kp_y[so]; l = p.kp_l[so]; score = p.kp_s[so];
+        if (p.use_tma) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, JSFE_WIN_BYTES + JSFE_DISC_BYTES);
+                tma_load_3d(win, &tm.win[l], bar, (x - JSFE_DP_R) & ~15, y - JSFE_DP_R, slot);
+                tma_load_3d(disc, &tm.disc[l], bar, (x - 15) & ~15, y - 15, slot);
+            }
+        } else {
+            const LevelGeom& lv = p.lv[l];
+            const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
+            const uint8_t* __restrict__ blr = lv.blur + (size_t)slot * lv.slot_stride;
+            const int wx0 = (x - JSFE_DP_R) & ~15, dx0 = (x - 15) & ~15;
+            for (int i = lane; i < JSFE_DP_ROWS * (JSFE_DP_PITCH / 4); i += 32) {
+                const int row = i / (JSFE_DP_PITCH / 4), wv = i - row * (JSFE_DP_PITCH / 4);
+                const int gy = y - JSFE_DP_R + row, gx = wx0 + 4 * wv;
+                uint32_t v = 0;
+                if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(blr + (size_t)gy * lv.pitch + gx));
+                *reinterpret_cast<uint32_t*>(win + row * JSFE_DP_PITCH + 4 * wv) = v;
+            }
+            for (int i = lane; i < JSFE_DISC_ROWS * (JSFE_DISC_PITCH / 4); i += 32) {
+                const int row = i / (JSFE_DISC_PITCH / 4), wv = i - row * (JSFE_DISC_PITCH / 4);
+                const int gy = y - 15 + row, gx = dx0 + 4 * wv;
+                uint32_t v = 0;
+                if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx));
+                *reinterpret_cast<uint32_t*>(disc + row * JSFE_DISC_PITCH + 4 * wv) = v;
+            }
+            __syncwarp();
         }
-    }
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { s_px[i] = p.tab->pat_x[i]; s_py[i] = p.tab->pat_y[i]; }
+    };
+
+    int x = 0, y = 0, l = 0, score = 0;
+    if (p.use_tma && lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (o0 < n) issue(o0, x, y, l, score);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_pat[i] = __ldg(&p.tab->pat_f[i]);
     __syncthreads();
-    if (o >= n) return;
-    if (p.use_tma) {
-        mbar_wait(&s_bar[warp], 0);
-    } else {
-        const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
-        const uint8_t* __restrict__ blr = lv.blur + (size_t)slot * lv.slot_stride;
-        for (int i = lane; i < JSFE_DP_ROWS * (JSFE_DP_PITCH / 4); i += 32) {
-            const int row = i / (JSFE_DP_PITCH / 4), wv = i - row * (JSFE_DP_PITCH / 4);
-            const int gy = y - JSFE_DP_R + row, gx = wx0 + 4 * wv;
-            uint32_t v = 0;
-            if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(blr + (size_t)gy * lv.pitch + gx));
-            *reinterpret_cast<uint32_t*>(win + row * JSFE_DP_PITCH + 4 * wv) = v;
-        }
-        for (int i = lane; i < JSFE_DISC_ROWS * (JSFE_DISC_PITCH / 4); i += 32) {
-            const int row = i / (JSFE_DISC_PITCH / 4), wv = i - row * (JSFE_DISC_PITCH / 4);
-            const int gy = y - 15 + row, gx = dx0 + 4 * wv;
-            uint32_t v = 0;
-            if (gy >= 0 && gy < lv.h && gx < lv.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * lv.pitch + gx));
-            *reinterpret_cast<uint32_t*>(disc + row * JSFE_DISC_PITCH + 4 * wv) = v;
-        }
-        __syncwarp();
-    }
+    // half-width table of the radius-15 disc, packed: nibble |u| = largest |v| whose row still contains column u
+    const unsigned long long vmax_tab = p.vmax_packed;
 
-    // intensity centroid over the radius-15 disc (integer moments; any summation order is exact); lane = column
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, au = abs(u);
-        const uint8_t* col = disc + 15 * JSFE_DISC_PITCH + (x - 15 - dx0) + lane;
-        int vmax = 0;   // largest |v| whose half-width reaches |u|
-#pragma unroll
-        for (int v = 0; v <= 15; ++v) vmax = (au <= p.tab->umax[v]) ? v : vmax;
-#pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            const int I = (abs(v) <= vmax) ? (int)col[v * JSFE_DISC_PITCH] : 0;
-            m10 += I;
-            m01 += v * I;
-        }
-        m10 *= u;
-    }
-    m10 = __reduce_add_sync(0xffffffffu, m10);
-    m01 = __reduce_add_sync(0xffffffffu, m01);
-    const float angle = atan2f((float)m01, (float)m10);
-    const float a = cosf(angle), b = sinf(angle);
+#pragma unroll 1
+    for (int k = 0; k < JSFE_KP_PER_WARP; ++k) {
+        const int o = o0 + k;
+        if (o >= n) break;
+        if (p.use_tma) mbar_wait(bar, (uint32_t)(k & 1));
+        const LevelGeom& lv = p.lv[l];
+        const int wx0 = (x - JSFE_DP_R) & ~15, dx0 = (x - 15) & ~15;   // x >= 20, so both are >= 0
 
-    // descriptor byte `lane`: 8 comparisons of blurred samples
-    const uint8_t* ctrb = win + JSFE_DP_R * JSFE_DP_PITCH + (x - wx0);
-    unsigned val = 0;
+        // intensity centroid over the radius-15 disc (integer moments; any summation order is exact); lane = column
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int u = lane - 15, au = abs(u);
+            const uint8_t* col = disc + 15 * JSFE_DISC_PITCH + (x - 15 - dx0) + lane;
+            const int vmax = (int)((vmax_tab >> (4 * au)) & 15ull);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int t[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int pi = lane * 16 + 2 * i + k;
-            const float fpx = (float)s_px[pi], fpy = (float)s_py[pi];
-            const int row = (int)rintf(__fmaf_rn(b, fpx, __fmul_rn(a, fpy)));
-            const int col = __float2int_rn(__fmaf_rn(a, fpx, -__fmul_rn(b, fpy)));
-            t[k] = ctrb[row * JSFE_DP_PITCH + col];
+            for (int v = -15; v <= 15; ++v) {
+                const int I = (abs(v) <= vmax) ? (int)col[v * JSFE_DISC_PITCH] : 0;
+                m10 += I;
+                m01 += v * I;
+            }
+            m10 *= u;
         }
-        val |= (unsigned)(t[0] < t[1]) << i;
-    }
-    p.desc[so * 32 + lane] = (uint8_t)val;
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        const float angle = atan2f((float)m01, (float)m10);
+        const float a = cosf(angle), b = sinf(angle);
 
-    if (lane == 0) {
-        int* kp = p.kps + (size_t)slot * 6 * p.cap;
-        const float sc = lv.scale;
-        kp[0 * p.cap + o] = __float2int_rz(__fmul_rn((float)x, sc));
-        kp[1 * p.cap + o] = __float2int_rz(__fmul_rn((float)y, sc));
-        kp[2 * p.cap + o] = score;
-        kp[3 * p.cap + o] = __float_as_int((float)((double)angle * (180.0 / 3.14159265358979323846)));
-        kp[4 * p.cap + o] = l;
-        kp[5 * p.cap + o] = __float2int_rz(__fmul_rn(31.0f, sc));
-        p.kp_angle[so] = angle;
+        // descriptor byte `lane`: 8 comparisons of blurred samples.  rintf via the 1.5*2^23 magic add (exact, no F2I)
+        const uint8_t* ctrb = win + JSFE_DP_R * JSFE_DP_PITCH + (x - wx0);
+        unsigned val = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int t[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float2 pt = s_pat[(2 * i + q) * 32 + lane];
+                const float fr = __fadd_rn(__fmaf_rn(b, pt.x, __fmul_rn(a, pt.y)), 12582912.0f);
+                const float fc = __fadd_rn(__fmaf_rn(a, pt.x, -__fmul_rn(b, pt.y)), 12582912.0f);
+                const int row = __float_as_int(fr) - 0x4B400000, col = __float_as_int(fc) - 0x4B400000;
+                t[q] = ctrb[row * JSFE_DP_PITCH + col];
+            }
+            val |= (unsigned)(t[0] < t[1]) << i;
+        }
+        // outputs of this keypoint
+        const size_t so = (size_t)slot * p.cap + o;
+        const int ox = x, oy = y, ol = l, oscore = score;
+        __syncwarp();                                   // every lane has finished reading win/disc
+        if (o + 1 < n && k + 1 < JSFE_KP_PER_WARP) issue(o + 1, x, y, l, score);   // next keypoint's boxes are in flight during the stores
+        p.desc[so * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            int* kp = p.kps + (size_t)slot * 6 * p.cap;
+            const float sc = lv.scale;
+            kp[0 * p.cap + o] = __float2int_rz(__fmul_rn((float)ox, sc));
+            kp[1 * p.cap + o] = __float2int_rz(__fmul_rn((float)oy, sc));
+            kp[2 * p.cap + o] = oscore;
+            kp[3 * p.cap + o] = __float_as_int((float)((double)angle * (180.0 / 3.14159265358979323846)));
+            kp[4 * p.cap + o] = ol;
+            kp[5 * p.cap + o] = __float2int_rz(__fmul_rn(31.0f, sc));
+            p.kp_angle[so] = angle;
+        }
     }
 }
 

@@ -41,6 +41,7 @@ struct DevTables {
     float gauss[49];           // 7x7 sigma=10 weights, row-major
     float sep_a[7], sep_b[7];  // separable factors: gauss[i*7+j] ~= sep_a[i]*sep_b[j] (|err| < 4e-9)
     int8_t pat_x[512], pat_y[512];
+    float2 pat_f[512];  // the same offsets as floats (x, y), transposed: entry [j*32 + b] = sample j (0..15) of descriptor byte b
     uint8_t col_rank[JSFE_MAXL][128];     // column priority of the reference's smem tree (0 wins ties)
     uint8_t col_by_rank[JSFE_MAXL][128];  // inverse permutation
 };
@@ -50,6 +51,7 @@ struct Params {
     int cap;        // max keypoints per slot (= number of NMS cells over all levels)
     int n_tile_rows;  // sum of n_tile_h
     int threshold;  // th_FAST_MAX
+    unsigned long long vmax_packed;  // nibble |u| (0..15) = largest |v| of the radius-15 disc whose row contains column u
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
     int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int H0, W0;
