@@ -773,7 +773,9 @@ __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params
 #define JSFE_WIN_SLOT 2432                                   // 2368 rounded up to 128
 #define JSFE_WARP_SMEM (JSFE_WIN_SLOT + 1536)                // + disc (1488 rounded up to 128)
 
-#define JSFE_KP_PER_WARP 1   // keypoints a warp processes one after the other (amortises the pattern staging)
+#ifndef JSFE_KP_PER_WARP
+#define JSFE_KP_PER_WARP 4   // keypoints a warp processes one after the other (amortises the pattern staging)
+#endif
 
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
     __shared__ __align__(128) uint8_t s_buf[8][JSFE_WARP_SMEM];
@@ -901,7 +903,10 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
 //     replaces the host loops + ORBGetDistanceStereoGPU + Compute_L1_distance_GPU + cublasSgemv of
 //     ORB_GPU::ORB_compute_stereo_match (src/cuda/orb_stereo_match.cu:105-561).
 // =================================================================================================
-__global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Params p, const __grid_constant__ RightSide rsd,
+#ifndef JSFE_SM_BLOCKS
+#define JSFE_SM_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(256, JSFE_SM_BLOCKS) k_stereo_match(const __grid_constant__ Params p, const __grid_constant__ RightSide rsd,
                                                       int pair0, int th_high, int th_low, float mb, float mbf) {
     const int pair = pair0 + blockIdx.y;
     const int sl = rsd.left_mul * pair + rsd.left_add, sr = rsd.right_mul * pair + rsd.right_add;
@@ -924,30 +929,44 @@ __global__ void __launch_bounds__(256) k_stereo_match(const __grid_constant__ Pa
     const uint8_t* descR = rsd.desc + (size_t)sr * cap * 32;
     const int* rs = rsd.row_start + (size_t)sr * (p.n_tile_rows + 1);
 
-    unsigned best = ((unsigned)th_high << 16) | 0xFFFFu;  // strict-min scan from TH_HIGH; ties -> lowest right index
-    for (int lr = max(0, lvl - 1); lr <= min(p.L - 1, lvl + 1); ++lr) {
-        const LevelGeom& g = p.lv[lr];
-        const float rho = __fmul_rn(2.0f, g.scale);
-        // conservative tile-row window of level lr that can reach row YL (exact test below)
-        int ylo = (int)floorf(((float)YL - rho - 1.0f) / g.scale) - 1;
-        int yhi = (int)ceilf(((float)YL + rho + 2.0f) / g.scale) + 1;
-        ylo = max(ylo, 0);
-        yhi = min(yhi, g.h - 1);
-        if (ylo > yhi) continue;
-        const int r0 = rs[g.tile_row_offset + ylo / g.tile_h];
-        const int r1 = rs[g.tile_row_offset + yhi / g.tile_h + 1];
-        for (int r = r0 + lane; r < r1; r += 32) {
-            const float yR = (float)kR[cap + r];
-            const int maxr = (int)ceilf(__fadd_rn(yR, rho)), minr = (int)floorf(__fsub_rn(yR, rho));
-            if (YL < minr || YL > maxr) continue;
-            const float uR = (float)kR[r];
-            if (!(uR >= minU && uR <= maxU)) continue;
-            const uint4* dr = reinterpret_cast<const uint4*>(descR + (size_t)r * 32);
-            const uint4 a = __ldg(dr), b = __ldg(dr + 1);
-            const int d = __popc(l0.x ^ a.x) + __popc(l0.y ^ a.y) + __popc(l0.z ^ a.z) + __popc(l0.w ^ a.w) +
-                          __popc(l1.x ^ b.x) + __popc(l1.y ^ b.y) + __popc(l1.z ^ b.z) + __popc(l1.w ^ b.w);
-            best = min(best, ((unsigned)d << 16) | (unsigned)r);
+    // lanes 0..2 work out the candidate range of levels lvl-1, lvl, lvl+1 in parallel (tile rows that can reach row YL;
+    // conservative, the exact row test is below); the three ranges are then scanned as one concatenated list
+    int c0 = 0, cn = 0;
+    float rho_l = 0.0f;
+    {
+        const int lr = lvl - 1 + lane;
+        if (lane < 3 && lr >= 0 && lr < p.L) {
+            const LevelGeom& g = p.lv[lr];
+            rho_l = __fmul_rn(2.0f, g.scale);
+            int ylo = (int)floorf(((float)YL - rho_l - 1.0f) / g.scale) - 1;
+            int yhi = (int)ceilf(((float)YL + rho_l + 2.0f) / g.scale) + 1;
+            ylo = max(ylo, 0);
+            yhi = min(yhi, g.h - 1);
+            if (ylo <= yhi) {
+                c0 = rs[g.tile_row_offset + ylo / g.tile_h];
+                cn = rs[g.tile_row_offset + yhi / g.tile_h + 1] - c0;
+            }
         }
+    }
+    const int b0 = __shfl_sync(0xffffffffu, c0, 0), b1 = __shfl_sync(0xffffffffu, c0, 1), b2 = __shfl_sync(0xffffffffu, c0, 2);
+    const int n0 = __shfl_sync(0xffffffffu, cn, 0), n1 = __shfl_sync(0xffffffffu, cn, 1), n2 = __shfl_sync(0xffffffffu, cn, 2);
+    const float rho0 = __shfl_sync(0xffffffffu, rho_l, 0), rho1 = __shfl_sync(0xffffffffu, rho_l, 1), rho2 = __shfl_sync(0xffffffffu, rho_l, 2);
+    const int n01 = n0 + n1, ntot = n01 + n2;
+
+    unsigned best = ((unsigned)th_high << 16) | 0xFFFFu;  // strict-min scan from TH_HIGH; ties -> lowest right index
+    for (int t = lane; t < ntot; t += 32) {
+        const int r = (t < n0) ? b0 + t : (t < n01) ? b1 + (t - n0) : b2 + (t - n01);
+        const float rho = (t < n0) ? rho0 : (t < n01) ? rho1 : rho2;
+        const int yRi = kR[cap + r], uRi = kR[r];
+        const float yR = (float)yRi, uR = (float)uRi;
+        const int maxr = (int)ceilf(__fadd_rn(yR, rho)), minr = (int)floorf(__fsub_rn(yR, rho));
+        if (YL < minr || YL > maxr) continue;
+        if (!(uR >= minU && uR <= maxU)) continue;
+        const uint4* dr = reinterpret_cast<const uint4*>(descR + (size_t)r * 32);
+        const uint4 a = __ldg(dr), b = __ldg(dr + 1);
+        const int d = __popc(l0.x ^ a.x) + __popc(l0.y ^ a.y) + __popc(l0.z ^ a.z) + __popc(l0.w ^ a.w) +
+                      __popc(l1.x ^ b.x) + __popc(l1.y ^ b.y) + __popc(l1.z ^ b.z) + __popc(l1.w ^ b.w);
+        best = min(best, ((unsigned)d << 16) | (unsigned)r);
     }
     best = __reduce_min_sync(0xffffffffu, best);
     const int bestD = (int)(best >> 16);

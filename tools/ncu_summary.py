@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read here, no GPU needed): headline metrics + hottest source lines.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--lines 25] [--src jsfe_kernels.cuh]"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--lines 25] [--by-inst]"""
 import csv, subprocess, sys, io, collections
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -53,7 +53,8 @@ def main():
     tot = sum(v[0] for v in per.values()) or 1
     toti = sum(v[1] for v in per.values()) or 1
     print(f'--- hottest source lines (of {tot} stall samples, {toti} warp-instructions)')
-    for (ln, txt), v in sorted(per.items(), key=lambda kv: -kv[1][0])[:nlines]:
+    key = 1 if '--by-inst' in sys.argv else 0
+    for (ln, txt), v in sorted(per.items(), key=lambda kv: -kv[1][key])[:nlines]:
         thr = v[2] / v[1] if v[1] else 0
         print(f'{100*v[0]/tot:5.1f}% smp {100*v[1]/toti:5.1f}% inst thr/inst {thr:4.1f}  L{ln:>4s}  {txt.strip()[:105]}')
 
