@@ -207,10 +207,10 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             g.tile_h = (int)((float)cfg->tile_h * inv[i]);
             g.tile_w = (int)((float)cfg->tile_w * inv[i]);
         }
-        // the reference divides by 128/tile_w (orb_FAST_apply_NMS_G.cu:1434); tile_h <= 256 is this library's key width
-        if (g.tile_w < 1 || g.tile_w > 128 || g.tile_h < 1 || g.tile_h > 256) {
+        // the reference divides by 128/tile_w (orb_FAST_apply_NMS_G.cu:1434); tile_h <= 254 is this library's key / work-list code width
+        if (g.tile_w < 1 || g.tile_w > 128 || g.tile_h < 1 || g.tile_h > 254) {
             delete h;
-            return fail(JSFE_ERR_INVALID, "level %d tile %dx%d unsupported (need 1<=tile_w<=128, 1<=tile_h<=256)", i, g.tile_h, g.tile_w);
+            return fail(JSFE_ERR_INVALID, "level %d tile %dx%d unsupported (need 1<=tile_w<=128, 1<=tile_h<=254)", i, g.tile_h, g.tile_w);
         }
         g.n_tile_h = (g.h - 1) / g.tile_h + 1;
         g.n_tile_w = (g.w - 1) / g.tile_w + 1;
@@ -233,6 +233,14 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const size_t gw = (size_t)g.cells_per_block * g.tile_w;
         const size_t pw = align_up(gw + 8 + 15, 16), pr = g.tile_h + 8;   // covers X0+GW+4-gx0 with gx0 = floor16(X0-4)
         g.tile_pw = (int)pw;
+        // phase A thread grid: 8-pixel column groups covering score columns [cs0-0, cs0+gw+1], cs0 = X0-1-floor16(X0-4) in [3,18]
+        int ngx = 1;
+        for (int cs0 = 3; cs0 <= 18; ++cs0) ngx = std::max(ngx, (int)((cs0 + gw + 1) >> 3) - (cs0 >> 3) + 1);
+        g.fast_ngx = ngx;
+        g.fast_nrl = std::max(1, 256 / ngx);
+        g.fast_ngx_inv = 65536u / (unsigned)ngx + 1u;
+        for (unsigned t = 0; t < 256; ++t)
+            if (((t * g.fast_ngx_inv) >> 16) != t / (unsigned)ngx) { delete h; return fail(JSFE_ERR_INVALID, "internal: phase A reciprocal is not exact"); }
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
         smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 9 / 4 + 64);  // pixels + scores + work list + positives (1/4)
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
@@ -344,7 +352,14 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         T->pat_y[i] = (int8_t)kPattern[2 * i + 1];
         T->pat_f[(i & 15) * 32 + (i >> 4)] = make_float2((float)T->pat_x[i], (float)T->pat_y[i]);  // [sample j][byte b]: bank-conflict-free per lane
     }
-    for (int i = 0; i < P.L; ++i) column_rank(P.lv[i].tile_w, T->col_rank[i], T->col_by_rank[i]);
+    for (int i = 0; i < P.L; ++i) {
+        const jsfe::LevelGeom& g = P.lv[i];
+        column_rank(g.tile_w, T->col_rank[i], T->col_by_rank[i]);
+        for (int c = 0; c < 192 && c < g.cells_per_block * g.tile_w; ++c)
+            T->colkey[i][c] = (uint16_t)(((127u - T->col_rank[i][c % g.tile_w]) << 8) | (unsigned)(c / g.tile_w));
+        for (int dy = 0; dy < g.tile_h && dy < 256; ++dy)
+            T->rowkey[i][dy] = (uint16_t)(((7u - (unsigned)(dy % g.T)) << 8) | (255u - (unsigned)dy));
+    }
 
     int rc = JSFE_OK;
     auto bail = [&](int code) { delete T; jsfe_destroy(h); return code; };
@@ -357,6 +372,20 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     P.tab = dT;
     delete T;
     T = nullptr;
+    {  // k_fast_cells work item -> (level, tile row, block in row)
+        std::vector<uint32_t> map((size_t)P.fast_items_total);
+        for (int i = 0; i < P.L; ++i) {
+            const jsfe::LevelGeom& g = P.lv[i];
+            for (int ty = 0; ty < g.n_tile_h; ++ty)
+                for (int bx = 0; bx < g.blocks_per_row; ++bx)
+                    map[(size_t)g.block_offset + (size_t)ty * g.blocks_per_row + bx] = ((uint32_t)i << 28) | ((uint32_t)ty << 14) | (uint32_t)bx;
+        }
+        uint32_t* d_map = nullptr;
+        if ((rc = dev_alloc(h, &d_map, map.size())) != JSFE_OK) return bail(rc);
+        if (cudaMemcpy(d_map, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(JSFE_ERR_CUDA, "work map upload failed"));
+        P.fast_map = d_map;
+    }
 
     // ---- images + masks
     const size_t M = (size_t)h->max_images, cap = (size_t)P.cap;

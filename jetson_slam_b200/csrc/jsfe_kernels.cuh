@@ -131,16 +131,13 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_best[192];
-    __shared__ uint16_t s_colkey[192];   // per owned column: (127 - priority rank) << 8 | cell index
-    __shared__ uint16_t s_rowkey[256];   // per owned row dy: (7 - dy % T) << 8 | (255 - dy)
     __shared__ int s_ncand, s_npos;
-    int l = 0;
-    while (l + 1 < p.L && (int)blockIdx.x >= p.lv[l + 1].block_offset) ++l;
+    const uint32_t item = __ldg(p.fast_map + blockIdx.x);   // level << 28 | tile row << 14 | block in row
+    const int l = (int)(item >> 28);
     const LevelGeom& lv = p.lv[l];
     const int slot = slot0 + blockIdx.y;
-    const int item = blockIdx.x - lv.block_offset;
-    const int ty = item / lv.blocks_per_row;
-    const int tx0 = (item - ty * lv.blocks_per_row) * lv.cells_per_block;
+    const int ty = (int)((item >> 14) & 0x3fffu);
+    const int tx0 = (int)(item & 0x3fffu) * lv.cells_per_block;
     const int ncells = min(lv.cells_per_block, lv.n_tile_w - tx0);
     const int X0 = tx0 * lv.tile_w, GW = ncells * lv.tile_w, y0 = ty * lv.tile_h;
     const int gx0 = ((X0 - 4) >> 4) << 4, gy0 = y0 - 4;
@@ -150,13 +147,13 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int SR = lv.tile_h + 2;
     uint8_t* pix = smem;
     uint16_t* sc = reinterpret_cast<uint16_t*>(smem + (size_t)PR * PW);
-    uint16_t* cand = sc + (size_t)SR * SW;
+    uint16_t* cand = sc + (size_t)SR * SW;           // work list of codes (score row << 8 | score column)
     uint16_t* pos = cand + (size_t)SR * SW;          // positives list (capacity = a quarter of the work list)
     const int pos_cap = (SR * SW) >> 2;
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
 
-    // ---- stage the pixel tile: one TMA box load (out-of-image rows/columns arrive as 0); meanwhile clear scores, build key tables
+    // ---- stage the pixel tile: one TMA box load (out-of-image rows/columns arrive as 0); meanwhile clear the scores
     if (p.use_tma) {
         if (tid == 0) {
             mbar_init(&s_bar, 1);
@@ -178,14 +175,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz = (SR * SW) >> 3;
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
-        if (tid < 192) {
-            s_best[tid] = 0;
-            if (tid < GW) {
-                const int cell = tid / lv.tile_w, j = tid - cell * lv.tile_w;
-                s_colkey[tid] = (uint16_t)(((127u - p.tab->col_rank[l][j]) << 8) | (unsigned)cell);
-            }
-        }
-        if (tid < lv.tile_h) s_rowkey[tid] = (uint16_t)(((7u - (unsigned)(tid % lv.T)) << 8) | (255u - (unsigned)tid));
+        if (tid < 192) s_best[tid] = 0;
         if (tid == 0) {
             s_ncand = 0;
             s_npos = 0;
@@ -195,26 +185,28 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     if (p.use_tma) mbar_wait(&s_bar, 0);  // TMA bytes have landed
 
     // ---- phase A: compass pre-test, 8 pixels (two 32-bit words) per thread and iteration;
-    //      thread = (column pair g, row lane rl); survivors go to the work list
+    //      thread = (column group g, row lane rl) on the level's fixed ngx x nrl grid; survivors go to the work list
     {
         const int cs0 = X0 - 1 - gx0;               // smem column of score column 0
-        const int g0 = cs0 >> 3, ngx = ((cs0 + GW + 1) >> 3) - g0 + 1;   // 8-pixel column pairs covering the score columns
-        int nrl = 256 / ngx;
-        if (nrl < 1) nrl = 1;                       // (ngx <= 26 by construction)
+        const int g0 = cs0 >> 3;                    // first 8-pixel column group that holds a score column
+        const int nrl = lv.fast_nrl;
         // score rows whose y lies in the interior [B, h-B): ry in [ry_lo, ry_hi)
         const int ry_lo = max(0, JSFE_B - (y0 - 1)), ry_hi = min(SR, lv.h - JSFE_B - (y0 - 1));
-        const int niter = (ry_hi - ry_lo + nrl - 1) / nrl;   // warp-uniform trip count: the list append is warp-collective
-        const int rl = tid / ngx, g = tid - rl * ngx;
+        const int rl = (int)(((unsigned)tid * lv.fast_ngx_inv) >> 16), g = tid - rl * lv.fast_ngx;
         const int c = (g0 + g) << 3, xb = gx0 + c;
         const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
-        // column validity masks of this thread's 2 x 4 pixels (MSB per byte), hoisted out of the row loop
+        // column validity masks of this thread's 2 x 4 pixels (MSB per byte), hoisted out of the row loop:
+        // bytes [lo, hi) of the 8-byte group are valid
         unsigned vma = 0, vmb = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            vma |= (unsigned)(xb + k >= xlo && xb + k <= xhi) << (8 * k + 7);
-            vmb |= (unsigned)(xb + 4 + k >= xlo && xb + 4 + k <= xhi) << (8 * k + 7);
+        {
+            const int lo = min(max(xlo - xb, 0), 8), hi = min(max(xhi - xb + 1, 0), 8);
+            if (hi > lo && rl < nrl) {
+                const unsigned long long ones = 0x8080808080808080ull;
+                const unsigned long long m = (hi == 8 ? ones : (ones & ((1ull << (8 * hi)) - 1ull))) & ~((1ull << (8 * lo)) - 1ull);
+                vma = (unsigned)m;
+                vmb = (unsigned)(m >> 32);
+            }
         }
-        if (rl >= nrl) { vma = 0; vmb = 0; }
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
         const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
         const int mode = p.compass_mode;
@@ -222,8 +214,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         int ry = ry_lo + rl;
         const uint8_t* rp = pix + (ry + 3) * PW + c;
         const uint8_t* mp = lv.mask ? lv.mask + (size_t)(y0 - 1 + ry) * lv.pitch + xb : nullptr;
-        int idx0 = ry * SW + (c - cs0);
-        const int rstep = nrl * PW, istep = nrl * SW;
+        int code0 = (ry << 8) + (c - cs0);          // work-list code of this thread's first pixel
+        const int rstep = nrl * PW, cstep = nrl << 8;
         const size_t mstep = (size_t)nrl * lv.pitch;
         // one 4-pixel group: v = centre pixels, P0/P8 = rows +3/-3, P4/P12 = columns +3/-3
         auto compass = [&](unsigned v, unsigned P0, unsigned P4, unsigned P8, unsigned P12) -> unsigned {
@@ -250,7 +242,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             }
             return cond & keep & 0x80808080u;
         };
-        for (int it = 0; it < niter; ++it, ry += nrl, rp += rstep, idx0 += istep) {
+        // block-uniform trip count (the list append is warp-collective)
+        for (int ry0 = ry_lo; ry0 < ry_hi; ry0 += nrl, ry += nrl, rp += rstep, code0 += cstep) {
             unsigned pa = 0, pb = 0;
             if ((vma | vmb) && ry < ry_hi) {
                 const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
@@ -280,14 +273,14 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 if (lane == 0) base = atomicAdd(&s_ncand, base);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 uint16_t* o = cand + base + pre;
-                if (pa & 0x00000080u) *o++ = (uint16_t)idx0;
-                if (pa & 0x00008000u) *o++ = (uint16_t)(idx0 + 1);
-                if (pa & 0x00800000u) *o++ = (uint16_t)(idx0 + 2);
-                if (pa & 0x80000000u) *o++ = (uint16_t)(idx0 + 3);
-                if (pb & 0x00000080u) *o++ = (uint16_t)(idx0 + 4);
-                if (pb & 0x00008000u) *o++ = (uint16_t)(idx0 + 5);
-                if (pb & 0x00800000u) *o++ = (uint16_t)(idx0 + 6);
-                if (pb & 0x80000000u) *o = (uint16_t)(idx0 + 7);
+                if (pa & 0x00000080u) *o++ = (uint16_t)code0;
+                if (pa & 0x00008000u) *o++ = (uint16_t)(code0 + 1);
+                if (pa & 0x00800000u) *o++ = (uint16_t)(code0 + 2);
+                if (pa & 0x80000000u) *o++ = (uint16_t)(code0 + 3);
+                if (pb & 0x00000080u) *o++ = (uint16_t)(code0 + 4);
+                if (pb & 0x00008000u) *o++ = (uint16_t)(code0 + 5);
+                if (pb & 0x00800000u) *o++ = (uint16_t)(code0 + 6);
+                if (pb & 0x80000000u) *o = (uint16_t)(code0 + 7);
             }
         }
     }
@@ -295,7 +288,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
 
     // ---- phase B: full ring evaluation of the survivors, dense, 4 ring points per packed word
     const int ncand = s_ncand;
-    const float inv_sw = 1.0f / (float)SW;
     {
         const uint32_t* __restrict__ lut = p.tab->lut_bits;
         const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
@@ -307,8 +299,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             int idx = 0;
           if (i < ncand) {
             idx = cand[i];
-            const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
-            const int rx = idx - ry * SW;
+            const int ry = idx >> 8, rx = idx & 255;
             const uint8_t* c = pix + (ry + 3) * PW + (cs0 + rx);
             const unsigned V = (unsigned)c[0] * 0x01010101u, nV7 = ~V & 0x7f7f7f7fu;
             // ring point k -> byte k%4 of word k/4   (offsets: orb_FAST_compute_score.cu:24-48)
@@ -330,7 +321,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             dark >>= 16;
             const unsigned hit = ((__ldg(lut + (bright >> 5)) >> (bright & 31)) | (__ldg(lut + (dark >> 5)) >> (dark & 31))) & 1u;
             score = hit ? sad : 0u;
-            sc[idx] = (uint16_t)score;
+            sc[ry * SW + rx] = (uint16_t)score;
           }
             // positives (about 40 % of the candidates) go to a second, smaller list so that phase C runs dense
             const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);
@@ -354,21 +345,20 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         const uint16_t* list = dense ? pos : cand;
         const int nlist = dense ? npos : ncand;
         for (int i = tid; i < nlist; i += 256) {
-            const int idx = list[i];
-            const unsigned s = sc[idx];
+            const int code = list[i];
+            const int ry = code >> 8, rx = code & 255;
+            const uint16_t* row = sc + ry * SW + rx;
+            const unsigned s = row[0];
             if (s) {
-                const int ry = __float2int_rz(__fmul_rn((float)idx + 0.5f, inv_sw));
-                const int rx = idx - ry * SW;
                 const int dy = ry - 1, xx = rx - 1, y = y0 + dy;
                 if (y >= ymin && y < ymax && xx >= 0 && xx < wv) {
-                    const uint16_t* row = sc + idx;
                     const uint16_t* up = row - SW;
                     const uint16_t* dn = row + SW;
                     const bool ok = s >= up[-1] && s >= up[0] && s >= up[1] && s >= row[-1] && s >= row[1] &&
                                     s >= dn[-1] && s >= dn[0] && s >= dn[1];
                     if (ok) {
-                        const unsigned ck = s_colkey[xx];
-                        const unsigned key = (s << 18) | ((ck >> 8) << 11) | (unsigned)s_rowkey[dy];
+                        const unsigned ck = __ldg(&p.tab->colkey[l][xx]);
+                        const unsigned key = (s << 18) | ((ck >> 8) << 11) | (unsigned)__ldg(&p.tab->rowkey[l][dy]);
                         atomicMax(&s_best[ck & 0xFFu], key);
                     }
                 }
@@ -904,7 +894,7 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
 //     ORB_GPU::ORB_compute_stereo_match (src/cuda/orb_stereo_match.cu:105-561).
 // =================================================================================================
 #ifndef JSFE_SM_BLOCKS
-#define JSFE_SM_BLOCKS 6
+#define JSFE_SM_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(256, JSFE_SM_BLOCKS) k_stereo_match(const __grid_constant__ Params p, const __grid_constant__ RightSide rsd,
                                                       int pair0, int th_high, int th_low, float mb, float mbf) {

@@ -24,6 +24,8 @@ struct LevelGeom {
     int tile_pw;                     // shared-memory pixel-tile pitch of k_fast_cells = TMA box width (multiple of 16)
     int blocks_per_row;              // ceil(n_tile_w / cells_per_block)
     int block_offset;                // first k_fast_cells work item of this level
+    int fast_ngx, fast_nrl;          // k_fast_cells phase A thread grid: 8-pixel column groups x row lanes (ngx*nrl <= 256)
+    unsigned fast_ngx_inv;           // floor(65536/ngx)+1: tid/ngx == (tid*inv)>>16 for tid < 256
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
     unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
     uint8_t* img;                    // level image of slot 0
@@ -44,6 +46,8 @@ struct DevTables {
     float2 pat_f[512];  // the same offsets as floats (x, y), transposed: entry [j*32 + b] = sample j (0..15) of descriptor byte b
     uint8_t col_rank[JSFE_MAXL][128];     // column priority of the reference's smem tree (0 wins ties)
     uint8_t col_by_rank[JSFE_MAXL][128];  // inverse permutation
+    uint16_t colkey[JSFE_MAXL][192];      // k_fast_cells: per owned column (127 - priority rank) << 8 | cell index in the block
+    uint16_t rowkey[JSFE_MAXL][256];      // per owned row dy: (7 - dy % T) << 8 | (255 - dy)
 };
 
 struct Params {
@@ -51,6 +55,7 @@ struct Params {
     int cap;        // max keypoints per slot (= number of NMS cells over all levels)
     int n_tile_rows;  // sum of n_tile_h
     int threshold;  // th_FAST_MAX
+    const uint32_t* fast_map;        // per k_fast_cells work item: level << 28 | tile row << 14 | block index in the row
     unsigned long long vmax_packed;  // nibble |u| (0..15) = largest |v| of the radius-15 disc whose row contains column u
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
     int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
