@@ -340,6 +340,18 @@ def run_ours(args, cfg):
     n_mean = float(res["n"].mean())
     d2h = int(res["bytes"])
     matched = int((res["u_right"][0::2] >= 0).sum())
+    # what the PCIe link alone gives for this step's input (pinned host -> device, nothing else running): the floor under e2e
+    dev_in = torch.empty_like(host, device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_in.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(3):
+        dev_in.copy_(host, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_ms = ev0.elapsed_time(ev1) / 3
+    del dev_in
 
     # single-pair latency (the reference's real-time use: one frame at a time), host images in -> host results out
     lat = None
@@ -398,7 +410,8 @@ def run_ours(args, cfg):
                                       (", NCCL gather of result slabs to rank 0 every step" if gather else "")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * cfg.height * cfg.width),
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e,
+                    "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": 2 * B * cfg.height * cfg.width / h2d_ms / 1e6},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": per_kernel[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, B if dom.startswith("k_stereo") else 2 * B), "peak_source": peak_src,

@@ -385,6 +385,19 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         if (cudaMemcpy(d_map, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(JSFE_ERR_CUDA, "work map upload failed"));
         P.fast_map = d_map;
+        std::vector<uint32_t> pm((size_t)std::max(P.pyr_blocks_total, 1));
+        for (int i = 1; i < P.L; ++i) {
+            const jsfe::LevelGeom& g = P.lv[i];
+            const int tiles_x = (g.pitch + 127) / 128, tiles_y = (g.h + 31) / 32;
+            for (int ty = 0; ty < tiles_y; ++ty)
+                for (int tx = 0; tx < tiles_x; ++tx)
+                    pm[(size_t)P.pyr_block_start[i] + (size_t)ty * tiles_x + tx] = ((uint32_t)i << 28) | ((uint32_t)ty << 14) | (uint32_t)tx;
+        }
+        uint32_t* d_pm = nullptr;
+        if ((rc = dev_alloc(h, &d_pm, pm.size())) != JSFE_OK) return bail(rc);
+        if (cudaMemcpy(d_pm, pm.data(), pm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(JSFE_ERR_CUDA, "work map upload failed"));
+        P.pyr_map = d_pm;
     }
 
     // ---- images + masks
@@ -837,7 +850,21 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
         CU(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
     }
     if (chunk_pairs < 1) chunk_pairs = 32;
-    const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+    // chunk schedule: a short first chunk (C/4, then C/2) so that compute starts early, full chunks after, and a short
+    // last chunk (C/2, C/4) so that little D2H is left when compute ends; the call is blocking, only its inside pipelines
+    std::vector<int> sizes;
+    {
+        int left = n_pairs;
+        const int ramp[2] = {std::max(1, chunk_pairs / 4), std::max(1, chunk_pairs / 2)};
+        const bool ramped = n_pairs >= 3 * chunk_pairs && !getenv("JSFE_NO_RAMP");
+        if (ramped)
+            for (int r = 0; r < 2; ++r) { sizes.push_back(ramp[r]); left -= ramp[r]; }
+        const int tail = ramped ? ramp[0] + ramp[1] : 0;
+        while (left - tail > 0) { const int c = std::min(chunk_pairs, left - tail); sizes.push_back(c); left -= c; }
+        if (ramped)
+            for (int r = 1; r >= 0; --r) { sizes.push_back(ramp[r]); left -= ramp[r]; }
+    }
+    const int n_chunks = (int)sizes.size();
     while ((int)h->ev_up.size() < n_chunks) {
         cudaEvent_t a, b;
         CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -848,8 +875,8 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
     const size_t cap = P.cap;
     const bool saved_prof = h->profiling;
     h->profiling = false;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int p0 = c * chunk_pairs, np = std::min(chunk_pairs, n_pairs - p0);
+    for (int c = 0, p0 = 0; c < n_chunks; p0 += sizes[c], ++c) {
+        const int np = sizes[c];
         const int s0 = 2 * p0, ns = 2 * np;
         // 1. one contiguous H2D per chunk (2-D copies with odd row widths run far below PCIe speed)
         CU(cudaMemcpyAsync(h->d_stage + img_bytes * s0, images + img_bytes * s0, img_bytes * ns, cudaMemcpyHostToDevice, h->st_h2d));

@@ -51,13 +51,11 @@ __device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(
 #define JSFE_PYR_ROWS 32   // rows per block tile (8 y-lanes x 4 rows each)
 
 __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params p, int slot0) {
-    int l = 1;
-    while (l + 1 < p.L && (int)blockIdx.x >= p.pyr_block_start[l + 1]) ++l;
+    const uint32_t item = __ldg(p.pyr_map + blockIdx.x);   // level << 28 | tile row << 14 | tile column
+    const int l = (int)(item >> 28);
     const LevelGeom& lv = p.lv[l];
     const int slot = slot0 + blockIdx.y;
-    const int bi = blockIdx.x - p.pyr_block_start[l];
-    const int tiles_x = (lv.pitch + 127) >> 7;
-    const int tyb = bi / tiles_x, txb = bi - tyb * tiles_x;
+    const int tyb = (int)((item >> 14) & 0x3fffu), txb = (int)(item & 0x3fffu);
     const int x4 = (txb << 7) + ((threadIdx.x & 31) << 2);
     if (x4 >= lv.pitch) return;
     const uint8_t* __restrict__ src = p.lv[0].img + (size_t)slot * p.lv[0].slot_stride;

@@ -55,6 +55,7 @@ struct Params {
     int cap;        // max keypoints per slot (= number of NMS cells over all levels)
     int n_tile_rows;  // sum of n_tile_h
     int threshold;  // th_FAST_MAX
+    const uint32_t* pyr_map;         // per k_pyramid block: level << 28 | tile row << 14 | tile column
     const uint32_t* fast_map;        // per k_fast_cells work item: level << 28 | tile row << 14 | block index in the row
     unsigned long long vmax_packed;  // nibble |u| (0..15) = largest |v| of the radius-15 disc whose row contains column u
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
