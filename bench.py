@@ -256,10 +256,13 @@ def run_ours(args, cfg):
             os.close(saved)
 
     B = args.pairs
-    fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
     # distinct synthetic pairs (rank-dependent seeds), cycled over the slots
     n_distinct = min(B, args.distinct)
     pairs = [synth.stereo_pair(cfg.height, cfg.width, 1000 * rank + s) for s in range(n_distinct)]
+    # colour only: the reference's own src/cuda on this GPU, timed before this process owns any device memory of ours
+    # (it allocates and frees per frame, which gets slower the more the process has mapped)
+    ref_cuda = ref_cuda_pairs_per_s(cfg, pairs[0]) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
     host = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
     for p in range(B):
@@ -423,8 +426,8 @@ def run_ours(args, cfg):
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample_pairs} C2 stereo pairs on {threads} threads ({cpu_dt:.1f} s wall)"},
         }
-        if not args.no_ref_cuda:
-            line["ref_cuda"] = ref_cuda_pairs_per_s(cfg, pairs[0])
+        if ref_cuda is not None:
+            line["ref_cuda"] = ref_cuda
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
