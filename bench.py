@@ -188,6 +188,37 @@ def ref_cuda_pairs_per_s(cfg, pair, iters=40):
         return {"unavailable": repr(e)[:200]}
 
 
+def sbp_microbench(iters=200):
+    """SURVEY.md 8(f1): ORBmatcher::SearchByProjection fused on the device, on the C4-sized synthetic problem (3412 keypoints),
+    timed with CUDA events (grid build + search per call) beside the CPU restatement (one thread) of the reference's host loops."""
+    import torch
+    from jetson_slam_b200 import frontend, synth
+    from oracle import oracle as orc
+    last, cur, R, t = synth.projection_scene(n_cur=3412, n_last=3412, seed=7)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dl, dc, dR, dt = {k: d(v) for k, v in last.items()}, {k: d(v) for k, v in cur.items()}, d(R), d(t)
+    sf = np.cumprod(np.array([1.0] + [1.2] * 7, np.float32)).astype(np.float32)
+    kw = dict(**synth.SBP_K, **synth.SBP_BOUNDS, mbf=synth.SBP_MBF, th=7.0, scale_factors=sf, level_mode=0)
+    for _ in range(10):
+        out = frontend.search_by_projection(dl, dc, dR, dt, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = frontend.search_by_projection(dl, dc, dR, dt, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / iters
+    t0 = time.perf_counter()
+    for _ in range(5):
+        want = orc.search_by_projection(last, cur, R, t, **kw)
+    cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    same = int(out["n_matches"].cpu()[0]) == want["nmatches"] and np.array_equal(out["cur_match"].cpu().numpy(), want["cur_match"])
+    return {"n_last": 3412, "n_cur": 3412, "matches": want["nmatches"], "device_ms_per_call": dev_ms, "cpu_port_ms_per_call": cpu_ms,
+            "identical_to_cpu_port": bool(same), "how": "jsfe_build_frame_grid + jsfe_search_by_projection (3 kernels + 3 memsets) per call, "
+            "device-resident inputs, CUDA events over %d calls; CPU = oracle restatement of the host loops, 1 thread" % iters}
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -372,7 +403,6 @@ def run_ours(args, cfg):
         ts = np.array(ts) * 1e3
         lat = {"pairs_in_flight": 1, "median_ms": float(np.median(ts)), "p95_ms": float(np.percentile(ts, 95)),
                "how": "jsfe_process_host_pairs(1 pair): pinned H2D + 10 kernels + D2H + sync, wall clock, 200 iterations"}
-        fe1.close()
 
     # per-kernel durations (CUDA events on the launching stream around every launch)
     fe.profile(True)
@@ -396,7 +426,52 @@ def run_ours(args, cfg):
     peak, peak_src = measured_hbm_peak()
     bpp = bytes_per_pair(levels, fe.max_kp)
 
+    def device_ladder():
+        # device-resident ladder: 1 / 8 / 64 pairs in flight, stream launches vs one CUDA-graph replay
+        sweep = {}
+        for nb in (1, 8, 64):
+            if nb > B:
+                continue
+
+            def small():
+                fe.extract(0, 2 * nb, stream)
+                fe.stereo_match(cfg.mb, cfg.mbf, 0, nb, stream=stream)
+
+            for _ in range(5):
+                small()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(50):
+                small()
+            e1.record(stream)
+            stream.synchronize()
+            ent = {"stream_ms": e0.elapsed_time(e1) / 50}
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    small()
+                for _ in range(5):
+                    g.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(50):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ent["graph_ms"] = e0.elapsed_time(e1) / 50
+                del g
+            except Exception as e:  # capture is optional colour
+                ent["graph_error"] = repr(e)[:160]
+                torch.cuda.synchronize()
+            ent["pairs_per_s"] = nb / (min(ent.get("graph_ms", 1e9), ent["stream_ms"]) / 1e3)
+            sweep[str(nb)] = ent
+        return sweep
+
+
     if rank == 0:
+        if lat is not None and world == 1:
+            lat["device_resident_ladder"] = device_ladder()
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, args.cpu_threads or 32))
         sample_pairs = 2 * threads
@@ -428,6 +503,11 @@ def run_ours(args, cfg):
         }
         if ref_cuda is not None:
             line["ref_cuda"] = ref_cuda
+        if world == 1:
+            try:
+                line["adjacent"] = {"search_by_projection": sbp_microbench()}
+            except Exception as e:   # adjacent-row colour must never break the headline line
+                line["adjacent"] = {"search_by_projection": {"error": repr(e)[:200]}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

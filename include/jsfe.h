@@ -188,6 +188,52 @@ int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, co
                     int max_x, int min_y, int max_y, int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz,
                     float* u, float* v, int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream);
 
+/* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) as ONE device
+ * pass (replaces the live branch src/ORBmatcher.cpp:1647-1963: 2 kernels + 3 host loops + 9 copies per call).
+ * All pointers are DEVICE pointers; work is enqueued on `stream`, not synchronised.
+ *
+ * jsfe_build_frame_grid replaces Frame::AssignFeaturesToGrid (src/Frame.cpp:464-479, PosInGrid :696-706): the 64x48 grid of the
+ * current frame as CSR -- cell_start[64*48+1], cell = ix*48+iy (mGrid[ix][iy]); cell_items[n_cur] lists keypoint indices,
+ * ascending inside a cell (the host's push_back order).  Build once per frame, reuse for every search against it. */
+#define JSFE_FRAME_GRID_COLS 64
+#define JSFE_FRAME_GRID_ROWS 48
+#define JSFE_HISTO_LENGTH 30
+int jsfe_build_frame_grid(int n_cur, const float* cur_x, const float* cur_y, float min_x, float max_x, float min_y, float max_y,
+                          int32_t* cell_start, int32_t* cell_items, void* stream);
+
+typedef struct jsfe_sbp_args {
+    /* last frame: the points the host loop keeps (map point present, not an outlier), in LastFrame order */
+    int32_t n_last;
+    const float *px, *py, *pz;      /* world positions (MapPoint::GetWorldPos)                        */
+    const int32_t* last_octave;     /* LastFrame.mvKeys[i].octave                                      */
+    const float* last_angle;        /* LastFrame.mvKeysUn[i].angle (degrees)                           */
+    const uint8_t* last_desc;       /* [n_last][32] MapPoint::GetDescriptor                            */
+    const float *rcw9, *tcw3;       /* CurrentFrame.mTcw rotation (row-major) and translation          */
+    float fx, fy, cx, cy, min_x, max_x, min_y, max_y; /* CurrentFrame intrinsics and image bounds (mnMinX ...) */
+    float mbf, th;                  /* CurrentFrame.mbf; search window factor (radius = th * scale_factors[octave]) */
+    float scale_factors[16];        /* CurrentFrame.mvScaleFactors                                     */
+    int32_t level_mode;             /* 0: levels octave-1..octave+1; 1: bForward (>= octave); 2: bBackward (<= octave) */
+    /* current frame */
+    int32_t n_cur;                  /* <= 65535                                                        */
+    const float *cur_x, *cur_y;     /* mvKeysUn[i].pt                                                  */
+    const int32_t* cur_octave;
+    const float* cur_angle;         /* degrees                                                         */
+    const float* cur_uright;        /* mvuRight (<= 0: monocular keypoint)                             */
+    const uint8_t* cur_occupied;    /* != 0 <=> mvpMapPoints[i] && Observations() > 0; NULL = none     */
+    const uint8_t* cur_desc;        /* [n_cur][32]                                                     */
+    const int32_t *cell_start, *cell_items; /* from jsfe_build_frame_grid                              */
+    int32_t th_high;                /* ORBmatcher::TH_HIGH (100); must be < 256                        */
+    int32_t check_orientation;      /* mbCheckOrientation                                              */
+    /* outputs */
+    int32_t* best_idx2;             /* [n_last] matched current keypoint, -1 = none (before the rotation cull) */
+    int32_t* best_dist;             /* [n_last] its Hamming distance, 256 = none                       */
+    int32_t* rot_bin;               /* [n_last] rotation-histogram bin, -1 = none                      */
+    int32_t* cur_match;             /* [n_cur] last-frame point whose map point the keypoint ends up with, -1 = none */
+    int32_t* hist;                  /* [30] rotation histogram sizes                                   */
+    int32_t* n_matches;             /* [1] the function's return value                                 */
+} jsfe_sbp_args;
+int jsfe_search_by_projection(const jsfe_sbp_args* args, void* stream);
+
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
 /* the 7x7-blurred level (descriptor input); zero outside [20,h-20)x[20,w-20) like the reference's image_gaussian_ */

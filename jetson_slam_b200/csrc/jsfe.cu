@@ -946,6 +946,48 @@ int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, co
     return JSFE_OK;
 }
 
+int jsfe_build_frame_grid(int n_cur, const float* cur_x, const float* cur_y, float min_x, float max_x, float min_y, float max_y,
+                          int32_t* cell_start, int32_t* cell_items, void* stream) {
+    if (n_cur < 0 || n_cur > 65535 || !cell_start || (n_cur && (!cur_x || !cur_y || !cell_items)) || !(max_x > min_x) || !(max_y > min_y))
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    const float winv = (float)JSFE_FRAME_GRID_COLS / (max_x - min_x), hinv = (float)JSFE_FRAME_GRID_ROWS / (max_y - min_y);  // Frame.cpp:234-235
+    jsfe::k_frame_grid<<<1, 1024, 0, (cudaStream_t)stream>>>(n_cur, cur_x, cur_y, min_x, min_y, winv, hinv, cell_start, cell_items);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
+int jsfe_search_by_projection(const jsfe_sbp_args* a, void* stream) {
+    if (!a || a->n_last < 0 || a->n_cur < 0 || a->n_cur > 65535 || a->th_high < 0 || a->th_high >= 256 || a->level_mode < 0 ||
+        a->level_mode > 2 || !a->n_matches || !a->hist || !(a->max_x > a->min_x) || !(a->max_y > a->min_y))
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    if (a->n_last && (!a->px || !a->py || !a->pz || !a->last_octave || !a->last_angle || !a->last_desc || !a->rcw9 || !a->tcw3 ||
+                      !a->best_idx2 || !a->best_dist || !a->rot_bin))
+        return fail(JSFE_ERR_INVALID, "null last-frame array");
+    if (a->n_cur && (!a->cur_x || !a->cur_y || !a->cur_octave || !a->cur_angle || !a->cur_uright || !a->cur_desc || !a->cell_start ||
+                     !a->cell_items || !a->cur_match))
+        return fail(JSFE_ERR_INVALID, "null current-frame array");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->n_cur) CU(cudaMemsetAsync(a->cur_match, 0xFF, (size_t)a->n_cur * sizeof(int32_t), st));   // -1
+    CU(cudaMemsetAsync(a->hist, 0, JSFE_HISTO_LENGTH * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(a->n_matches, 0, sizeof(int32_t), st));
+    if (a->n_last == 0) return JSFE_OK;
+    if (a->n_cur == 0) {   // nothing to match against: every point reports "none"
+        CU(cudaMemsetAsync(a->best_idx2, 0xFF, (size_t)a->n_last * sizeof(int32_t), st));
+        CU(cudaMemsetAsync(a->rot_bin, 0xFF, (size_t)a->n_last * sizeof(int32_t), st));
+        std::vector<int32_t> none((size_t)a->n_last, 256);
+        CU(cudaMemcpyAsync(a->best_dist, none.data(), none.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // `none` is a stack-owned buffer
+        return JSFE_OK;
+    }
+    jsfe::k_sbp_match<<<(a->n_last + 7) / 8, 256, 0, st>>>(*a);
+    CU(cudaGetLastError());
+    if (a->check_orientation) {
+        jsfe::k_sbp_finish<<<1, 1024, 0, st>>>(*a);
+        CU(cudaGetLastError());
+    }
+    return JSFE_OK;
+}
+
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst) {
     int rc = check_slots(h, slot, 1);
     if (rc) return rc;

@@ -1122,6 +1122,197 @@ __global__ void __launch_bounds__(256) k_project_points(int n, const float* __re
     u[i] = uu; v[i] = vv; invz[i] = iz; is_valid[i] = ok;
 }
 
+// =================================================================================================
+// the whole of ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) on the device
+// (src/ORBmatcher.cpp:1647-1963): projection -> 64x48 grid window (Frame::GetFeaturesInArea, src/Frame.cpp:569-639)
+// -> Hamming arg-min -> rotation histogram -> ComputeThreeMaxima cull.  The reference does this with 2 kernels,
+// 3 host loops and 9 copies per call; here: k_frame_grid once per frame, then k_sbp_match + k_sbp_finish per call.
+// The host's sequential semantics are kept by construction: arg-min ties go to the lowest CSR position (= the host's
+// candidate order: cell column, cell row, insertion order), a keypoint claimed by several points keeps the highest
+// point index (= the last assignment), and the cull runs in a second kernel after all assignments.
+// =================================================================================================
+#define JSFE_GRID_COLS JSFE_FRAME_GRID_COLS
+#define JSFE_GRID_ROWS JSFE_FRAME_GRID_ROWS
+#define JSFE_GRID_CELLS (JSFE_GRID_COLS * JSFE_GRID_ROWS)
+
+typedef ::jsfe_sbp_args SbpArgs;   // the public argument block (include/jsfe.h) is passed to the kernels by value
+
+__device__ __forceinline__ int grid_cell_of(float x, float y, float min_x, float min_y, float winv, float hinv) {
+    const int cx = (int)roundf(__fmul_rn(__fsub_rn(x, min_x), winv)), cy = (int)roundf(__fmul_rn(__fsub_rn(y, min_y), hinv));
+    return (cx < 0 || cx >= JSFE_GRID_COLS || cy < 0 || cy >= JSFE_GRID_ROWS) ? -1 : cx * JSFE_GRID_ROWS + cy;
+}
+
+// Frame::AssignFeaturesToGrid (src/Frame.cpp:464-479) as CSR: one block; counts by the whole block, exclusive scan,
+// then warp 0 walks the keypoints in order (match_any gives the rank among equal cells) so every cell lists ascending indices
+__global__ void __launch_bounds__(1024) k_frame_grid(int n, const float* __restrict__ x, const float* __restrict__ y, float min_x,
+                                                     float min_y, float winv, float hinv, int* __restrict__ cell_start,
+                                                     int* __restrict__ cell_items) {
+    __shared__ int s_cnt[JSFE_GRID_CELLS];
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < JSFE_GRID_CELLS; c += 1024) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = grid_cell_of(x[i], y[i], min_x, min_y, winv, hinv);
+        if (c >= 0) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counters: 3 per thread, warp scan, then scan of the 32 warp totals
+    const int c0 = s_cnt[3 * tid], c1 = s_cnt[3 * tid + 1], c2 = s_cnt[3 * tid + 2];
+    int incl = c0 + c1 + c2;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        s_warp[lane] = w;   // inclusive
+    }
+    __syncthreads();
+    const int base = (warp ? s_warp[warp - 1] : 0) + incl - (c0 + c1 + c2);
+    cell_start[3 * tid] = base;
+    cell_start[3 * tid + 1] = base + c0;
+    cell_start[3 * tid + 2] = base + c0 + c1;
+    if (tid == 1023) cell_start[JSFE_GRID_CELLS] = base + c0 + c1 + c2;
+    __syncthreads();
+    s_cnt[3 * tid] = base;              // becomes the running fill position of every cell
+    s_cnt[3 * tid + 1] = base + c0;
+    s_cnt[3 * tid + 2] = base + c0 + c1;
+    __syncthreads();
+    if (warp == 0) {
+        for (int b = 0; b < n; b += 32) {
+            const int i = b + lane;
+            const int c = i < n ? grid_cell_of(x[i], y[i], min_x, min_y, winv, hinv) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, c);
+            const int leader = __ffs(peers) - 1;
+            int pos = 0;
+            if (c >= 0 && lane == leader) { pos = s_cnt[c]; s_cnt[c] = pos + __popc(peers); }
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (c >= 0) cell_items[pos + __popc(peers & ((1u << lane) - 1u))] = i;
+            __syncwarp();
+        }
+    }
+}
+
+// one warp per last-frame point
+__global__ void __launch_bounds__(256) k_sbp_match(const __grid_constant__ SbpArgs a) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= a.n_last) return;
+    int out_idx = -1, out_dist = 256, out_bin = -1;
+    // projection: the arithmetic of k_project_points (src/cuda/orb_matcher.cu:17-64)
+    const float X = dot3_plus(a.px[i], __ldg(a.rcw9 + 0), a.py[i], __ldg(a.rcw9 + 1), a.pz[i], __ldg(a.rcw9 + 2), __ldg(a.tcw3 + 0));
+    const float Y = dot3_plus(a.px[i], __ldg(a.rcw9 + 3), a.py[i], __ldg(a.rcw9 + 4), a.pz[i], __ldg(a.rcw9 + 5), __ldg(a.tcw3 + 1));
+    const float Z = dot3_plus(a.px[i], __ldg(a.rcw9 + 6), a.py[i], __ldg(a.rcw9 + 7), a.pz[i], __ldg(a.rcw9 + 8), __ldg(a.tcw3 + 2));
+    bool ok = false;
+    float x = 0.f, y = 0.f, iz = 0.f;
+    if (Z > 0.0f) {
+        iz = __frcp_rn(Z);
+        x = __fmaf_rn(__fmul_rn(X, a.fx), iz, a.cx);
+        y = __fmaf_rn(__fmul_rn(Y, a.fy), iz, a.cy);
+        ok = !(x < a.min_x || x > a.max_x || y < a.min_y || y > a.max_y);
+    }
+    if (ok) {
+        const int lo = a.last_octave[i];
+        const float r = __fmul_rn(a.th, a.scale_factors[lo]);
+        const int min_level = a.level_mode == 1 ? lo : a.level_mode == 2 ? 0 : lo - 1;
+        const int max_level = a.level_mode == 1 ? -1 : a.level_mode == 2 ? lo : lo + 1;
+        const float winv = __fdiv_rn((float)JSFE_GRID_COLS, __fsub_rn(a.max_x, a.min_x));
+        const float hinv = __fdiv_rn((float)JSFE_GRID_ROWS, __fsub_rn(a.max_y, a.min_y));
+        const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, a.min_x), r), winv)));
+        const int cx1 = min(JSFE_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, a.min_x), r), winv)));
+        const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, a.min_y), r), hinv)));
+        const int cy1 = min(JSFE_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, a.min_y), r), hinv)));
+        if (cx0 < JSFE_GRID_COLS && cx1 >= 0 && cy0 < JSFE_GRID_ROWS && cy1 >= 0) {
+            const bool check_levels = (min_level > 0) || (max_level >= 0);
+            const uint4* dl = reinterpret_cast<const uint4*>(a.last_desc + (size_t)i * 32);
+            const uint4 l0 = __ldg(dl), l1 = __ldg(dl + 1);
+            const float ur = __fsub_rn(x, __fmul_rn(a.mbf, iz));
+            unsigned best = (256u << 16) | 0xFFFFu;
+            for (int ix = cx0; ix <= cx1; ++ix) {      // cells (ix, cy0..cy1) are contiguous in the CSR
+                const int j0 = __ldg(a.cell_start + ix * JSFE_GRID_ROWS + cy0), j1 = __ldg(a.cell_start + ix * JSFE_GRID_ROWS + cy1 + 1);
+                for (int j = j0 + lane; j < j1; j += 32) {
+                    const int idx = __ldg(a.cell_items + j);
+                    const int oc = a.cur_octave[idx];
+                    if (check_levels && (oc < min_level || (max_level >= 0 && oc > max_level))) continue;
+                    const float dx = __fsub_rn(a.cur_x[idx], x), dy = __fsub_rn(a.cur_y[idx], y);
+                    if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;
+                    if (a.cur_occupied != nullptr && a.cur_occupied[idx]) continue;
+                    const float cu = a.cur_uright[idx];
+                    if (cu > 0.0f && fabsf(__fsub_rn(ur, cu)) > r) continue;
+                    const uint4* dr = reinterpret_cast<const uint4*>(a.cur_desc + (size_t)idx * 32);
+                    const uint4 p = __ldg(dr), q = __ldg(dr + 1);
+                    const int d = __popc(l0.x ^ p.x) + __popc(l0.y ^ p.y) + __popc(l0.z ^ p.z) + __popc(l0.w ^ p.w) +
+                                  __popc(l1.x ^ q.x) + __popc(l1.y ^ q.y) + __popc(l1.z ^ q.z) + __popc(l1.w ^ q.w);
+                    best = min(best, ((unsigned)d << 16) | (unsigned)j);   // ties -> lowest CSR position = host order
+                }
+            }
+            best = __reduce_min_sync(0xffffffffu, best);
+            const int bd = (int)(best >> 16);
+            if (bd <= a.th_high && (best & 0xFFFFu) != 0xFFFFu) {
+                out_idx = __ldg(a.cell_items + (best & 0xFFFFu));
+                out_dist = bd;
+                if (a.check_orientation) {
+                    float rot = __fsub_rn(a.last_angle[i], a.cur_angle[out_idx]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int bin = (int)roundf(__fmul_rn(rot, 1.0f / JSFE_HISTO_LENGTH));
+                    if (bin == JSFE_HISTO_LENGTH) bin = 0;
+                    out_bin = bin;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        a.best_idx2[i] = out_idx;
+        a.best_dist[i] = out_dist;
+        a.rot_bin[i] = out_bin;
+        if (out_idx >= 0) {
+            atomicMax(a.cur_match + out_idx, i);      // the host's last assignment wins
+            atomicAdd(a.n_matches, 1);
+            if (out_bin >= 0) atomicAdd(a.hist + out_bin, 1);
+        }
+    }
+}
+
+// ComputeThreeMaxima (src/ORBmatcher.cpp:2097-2138) + the cull loop (:1940-1955); one block
+__global__ void __launch_bounds__(1024) k_sbp_finish(const __grid_constant__ SbpArgs a) {
+    __shared__ int s_ind[3];
+    __shared__ int s_culled;
+    if (threadIdx.x == 0) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int b = 0; b < JSFE_HISTO_LENGTH; ++b) {
+            const int s = a.hist[b];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = b; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = b; }
+            else if (s > max3) { max3 = s; ind3 = b; }
+        }
+        if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+        else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+        s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+        s_culled = 0;
+    }
+    __syncthreads();
+    const int i1 = s_ind[0], i2 = s_ind[1], i3 = s_ind[2];
+    int culled = 0;
+    for (int i = threadIdx.x; i < a.n_last; i += blockDim.x) {
+        const int b = a.rot_bin[i];
+        if (b >= 0 && b != i1 && b != i2 && b != i3) {
+            a.cur_match[a.best_idx2[i]] = -1;
+            ++culled;
+        }
+    }
+    if (culled) atomicAdd(&s_culled, culled);
+    __syncthreads();
+    if (threadIdx.x == 0) *a.n_matches -= s_culled;
+}
+
 __global__ void __launch_bounds__(256) k_hamming_pairs(int n, const int* __restrict__ idx_l, const int* __restrict__ idx_r,
                                                        const uint8_t* __restrict__ desc_l, const uint8_t* __restrict__ desc_r,
                                                        int* __restrict__ dist) {

@@ -84,6 +84,8 @@ def lib():
         L.jsfe_project_points.argtypes = [C.c_int] + [vp] * 5 + [f] * 8 + [vp] * 4 + [vp]
         L.jsfe_hamming_pairs.argtypes = [C.c_int] + [vp] * 5 + [vp]
         L.jsfe_in_frustum.argtypes = [C.c_int] + [vp] * 12 + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
+        L.jsfe_build_frame_grid.argtypes = [C.c_int, vp, vp, f, f, f, f, vp, vp, vp]
+        L.jsfe_search_by_projection.argtypes = [vp, vp]
         L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_level_blur.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -357,3 +359,68 @@ def in_frustum(P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow, fx, fy, cx, 
                                  max_y, n_levels, log_scale_factor, view_cos_angle, _ptr(iz), _ptr(u), _ptr(v), _ptr(lvl), _ptr(vc),
                                  _ptr(ok), _stream_ptr(stream)))
     return iz, u, v, lvl, vc, ok
+
+
+# ---------------------------------------------------------------------------------------------------- SURVEY 8(f1)
+class _SbpArgs(C.Structure):
+    """ctypes image of jsfe_sbp_args (include/jsfe.h)."""
+    _fields_ = ([("n_last", C.c_int32)] + [(n, C.c_void_p) for n in ("px", "py", "pz", "last_octave", "last_angle", "last_desc", "rcw9", "tcw3")] +
+                [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "min_x", "max_x", "min_y", "max_y", "mbf", "th")] +
+                [("scale_factors", C.c_float * 16), ("level_mode", C.c_int32), ("n_cur", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("cur_x", "cur_y", "cur_octave", "cur_angle", "cur_uright", "cur_occupied", "cur_desc",
+                                           "cell_start", "cell_items")] +
+                [("th_high", C.c_int32), ("check_orientation", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("best_idx2", "best_dist", "rot_bin", "cur_match", "hist", "n_matches")])
+
+
+FRAME_GRID_COLS, FRAME_GRID_ROWS, HISTO_LENGTH = 64, 48, 30
+
+
+def build_frame_grid(cur_x, cur_y, min_x, max_x, min_y, max_y, stream=None):
+    """Device Frame::AssignFeaturesToGrid (src/Frame.cpp:464-479): -> (cell_start int32[64*48+1], cell_items int32[n]) CUDA tensors."""
+    import torch
+    n = cur_x.shape[0]
+    start = torch.empty(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, dtype=torch.int32, device=cur_x.device)
+    items = torch.full((max(n, 1),), -1, dtype=torch.int32, device=cur_x.device)
+    _check(lib().jsfe_build_frame_grid(n, _ptr(cur_x), _ptr(cur_y), float(min_x), float(max_x), float(min_y), float(max_y),
+                                       _ptr(start), _ptr(items), _stream_ptr(stream)))
+    return start, items
+
+
+def search_by_projection(last, cur, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_y, max_y, mbf, th, scale_factors, level_mode,
+                         th_high=100, check_orientation=True, grid=None, stream=None):
+    """Device ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cpp:1647-1963) in one pass.
+    last: dict of CUDA tensors P [3,n] f32, octave i32, angle f32 (deg), desc u8 [n,32];
+    cur : dict of CUDA tensors x, y f32, octave i32, angle f32, uright f32, occupied u8 (or None), desc u8 [m,32];
+    level_mode 0/1/2 = neither / bForward / bBackward.  grid: result of build_frame_grid (built here when None).
+    -> dict of CUDA tensors best_idx2, best_dist, rot_bin [n], cur_match [m], hist [30], n_matches [1] (no synchronisation)."""
+    import torch
+    P = last["P"]
+    dev = P.device
+    n, m = P.shape[1], cur["x"].shape[0]
+    if grid is None:
+        grid = build_frame_grid(cur["x"], cur["y"], min_x, max_x, min_y, max_y, stream)
+    out = dict(best_idx2=torch.empty(max(n, 1), dtype=torch.int32, device=dev), best_dist=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
+               rot_bin=torch.empty(max(n, 1), dtype=torch.int32, device=dev), cur_match=torch.empty(max(m, 1), dtype=torch.int32, device=dev),
+               hist=torch.empty(HISTO_LENGTH, dtype=torch.int32, device=dev), n_matches=torch.empty(1, dtype=torch.int32, device=dev))
+    a = _SbpArgs()
+    a.n_last, a.n_cur = n, m
+    a.px, a.py, a.pz = _ptr(P[0]), _ptr(P[1]), _ptr(P[2])
+    a.last_octave, a.last_angle, a.last_desc = _ptr(last["octave"]), _ptr(last["angle"]), _ptr(last["desc"])
+    a.rcw9, a.tcw3 = _ptr(Rcw), _ptr(tcw)
+    a.fx, a.fy, a.cx, a.cy, a.min_x, a.max_x, a.min_y, a.max_y, a.mbf, a.th = fx, fy, cx, cy, min_x, max_x, min_y, max_y, mbf, th
+    sf = np.zeros(16, np.float32)
+    sf[:len(scale_factors)] = np.asarray(scale_factors, np.float32)
+    a.scale_factors = (C.c_float * 16)(*sf.tolist())
+    a.level_mode = int(level_mode)
+    a.cur_x, a.cur_y, a.cur_octave, a.cur_angle = _ptr(cur["x"]), _ptr(cur["y"]), _ptr(cur["octave"]), _ptr(cur["angle"])
+    a.cur_uright, a.cur_desc = _ptr(cur["uright"]), _ptr(cur["desc"])
+    a.cur_occupied = _ptr(cur["occupied"]) if cur.get("occupied") is not None else None
+    a.cell_start, a.cell_items = _ptr(grid[0]), _ptr(grid[1])
+    a.th_high, a.check_orientation = int(th_high), int(bool(check_orientation))
+    for k in ("best_idx2", "best_dist", "rot_bin", "cur_match", "hist", "n_matches"):
+        setattr(a, k, _ptr(out[k]))
+    _check(lib().jsfe_search_by_projection(C.byref(a), _stream_ptr(stream)))
+    out["best_idx2"], out["best_dist"], out["rot_bin"], out["cur_match"] = out["best_idx2"][:n], out["best_dist"][:n], out["rot_bin"][:n], out["cur_match"][:m]
+    out["grid"] = grid
+    return out

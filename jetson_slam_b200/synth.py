@@ -9,6 +9,8 @@ so that left<->right matches exist.  Pure NumPy, deterministic for a given (seed
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 
@@ -82,3 +84,53 @@ def degenerate_images(height: int, width: int) -> dict[str, np.ndarray]:
         "checker": (((yy // 8) + (xx // 8)) % 2 * 200 + 20).astype(np.uint8),
     }
     return {k: np.ascontiguousarray(v) for k, v in out.items()}
+
+
+# ---- a synthetic SearchByProjection problem (KITTI-like intrinsics) ----
+SBP_K = dict(fx=718.856, fy=718.856, cx=607.19, cy=185.2)
+SBP_BOUNDS = dict(min_x=0.0, max_x=1241.0, min_y=0.0, max_y=376.0)
+SBP_MBF = 386.1448
+
+
+def projection_scene(n_cur=1500, n_last=1200, seed=0, noise_px=3.0, clustered=False, dup_desc=False):
+    """A current frame (keypoints on a pixel grid, random descriptors) and last-frame map points that project near a
+    subset of them under a small camera motion; descriptors differ by a few bits so that matches exist."""
+    rng = np.random.default_rng(seed)
+    if clustered:   # everything inside two grid cells: long candidate lists, many ties
+        x = rng.integers(300, 330, size=n_cur).astype(np.float32)
+        y = rng.integers(100, 112, size=n_cur).astype(np.float32)
+    else:
+        x = rng.integers(5, 1236, size=n_cur).astype(np.float32)
+        y = rng.integers(5, 371, size=n_cur).astype(np.float32)
+    octave = rng.integers(0, 8, size=n_cur).astype(np.int32)
+    angle = rng.uniform(0, 360, size=n_cur).astype(np.float32)
+    desc = rng.integers(0, 256, size=(n_cur, 32), dtype=np.uint8)
+    if dup_desc:
+        desc[:] = desc[0]
+    uright = np.where(rng.random(n_cur) < 0.6, x - rng.uniform(2, 60, size=n_cur), -1.0).astype(np.float32)
+    occupied = (rng.random(n_cur) < 0.15).astype(np.uint8)
+    cur = dict(x=x, y=y, octave=octave, angle=angle, uright=uright, occupied=occupied, desc=desc)
+    # camera pose of the current frame
+    a = 0.02
+    R = np.array([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]], np.float32)
+    t = np.array([0.05, -0.02, 0.3], np.float32)
+    src = rng.integers(0, n_cur, size=n_last)
+    z = np.where(uright[src] > 0, SBP_MBF / np.maximum(x[src] - uright[src], 0.5), rng.uniform(4, 60, size=n_last)).astype(np.float64)
+    z[rng.random(n_last) < 0.03] *= -1                      # some behind the camera
+    u = x[src] + rng.normal(0, noise_px, size=n_last)
+    v = y[src] + rng.normal(0, noise_px, size=n_last)
+    Pc = np.stack([(u - SBP_K["cx"]) * z / SBP_K["fx"], (v - SBP_K["cy"]) * z / SBP_K["fy"], z])
+    Pw = (R.astype(np.float64).T @ (Pc - t[:, None].astype(np.float64))).astype(np.float32)
+    ld = desc[src].copy()
+    flips = rng.integers(0, 256, size=(n_last, 6))
+    for i in range(n_last):
+        for b in flips[i, : rng.integers(0, 7)]:
+            ld[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    strangers = rng.random(n_last) < 0.1
+    ld[strangers] = rng.integers(0, 256, size=(int(strangers.sum()), 32), dtype=np.uint8)
+    la = (angle[src] + np.where(rng.random(n_last) < 0.8, rng.normal(5, 3, size=n_last), rng.uniform(-180, 180, size=n_last))).astype(np.float32) % np.float32(360)
+    lo = np.clip(octave[src] + rng.integers(-1, 2, size=n_last), 0, 7).astype(np.int32)
+    last = dict(P=Pw, octave=lo, angle=la.astype(np.float32), desc=ld)
+    return last, cur, R.ravel().copy(), t
+
+

@@ -25,8 +25,9 @@
  * src/cuda compiled unmodified for sm_100a (oracle/ref_build -> oracle/_ref)
  * and run on a B200; the resulting vectors are committed under tests/golden/ref_*.npz
  * (tools/make_golden.py; report: tests/golden/pin_report_r1_run*.json -- every stage bit-identical).
- * Status: PINNED for the extraction + stereo path.  The three adjacent helpers at the end of this file are
- * checked against the reference kernels on the GPU box by tests/test_gpu_helpers.py (no committed fixture).
+ * Status: PINNED for the extraction + stereo path.  The three adjacent helper kernels (projection, Hamming pairs,
+ * frustum) are checked against the reference kernels on the GPU box by tests/test_helpers.py (no committed fixture).
+ * orc_search_by_projection (row f1) restates reference HOST code that cannot be built here: parity UNPINNED for it.
  */
 #ifndef JSFE_ORACLE_H
 #define JSFE_ORACLE_H
@@ -143,6 +144,21 @@ void orc_in_frustum(int n, const float* px, const float* py, const float* pz, co
                     float fy, float cx, float cy, int min_x, int max_x, int min_y, int max_y, int n_scale_levels,
                     float log_scale_factor, float view_cos_angle, float* invz, float* u, float* v,
                     int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum);
+
+/* ---- the live branch of ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+ * (src/ORBmatcher.cpp:1647-1963) with Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cpp:464-479, 569-639) and
+ * ComputeThreeMaxima (src/ORBmatcher.cpp:2097-2138).  Restatement only (the host code around the two pinned kernels cannot
+ * be compiled here): parity UNPINNED for the host loops. */
+void orc_assign_features_to_grid(int n, const float* x, const float* y, float min_x, float min_y, float winv, float hinv,
+                                 int32_t* cell_start /* 64*48+1 */, int32_t* cell_items /* n */);
+int orc_search_by_projection(int n_last, const float* px, const float* py, const float* pz, const int32_t* last_octave,
+                             const float* last_angle, const uint8_t* last_desc, const float* rcw9, const float* tcw3,
+                             float fx, float fy, float cx, float cy, float min_x, float max_x, float min_y, float max_y,
+                             float mbf, float th, const float* scale_factors, int level_mode, int n_cur,
+                             const float* cur_x, const float* cur_y, const int32_t* cur_octave, const float* cur_angle,
+                             const float* cur_uright, const uint8_t* cur_occupied, const uint8_t* cur_desc, int th_high,
+                             int check_orientation, int32_t* best_idx2, int32_t* best_dist, int32_t* rot_bin,
+                             int32_t* cur_match, int32_t* hist /* 30 */);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,9 @@ def lib():
         L.orc_project_points.argtypes = [ci] + [vpp] * 5 + [f] * 8 + [vpp] * 4
         L.orc_hamming_pairs.argtypes = [ci] + [vpp] * 5
         L.orc_in_frustum.argtypes = [ci] + [vpp] * 12 + [f] * 4 + [ci] * 5 + [f] * 2 + [vpp] * 6
+        L.orc_assign_features_to_grid.argtypes = [ci, vpp, vpp, f, f, f, f, vpp, vpp]
+        L.orc_search_by_projection.restype = ci
+        L.orc_search_by_projection.argtypes = [ci] + [vpp] * 8 + [f] * 10 + [vpp, ci, ci] + [vpp] * 7 + [ci, ci] + [vpp] * 5
         _lib = L
     return _lib
 
@@ -218,3 +221,38 @@ def in_frustum(P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow, fx, fy, cx, 
                          Ow.ctypes.data, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels, log_scale_factor, view_cos_angle,
                          iz.ctypes.data, u.ctypes.data, v.ctypes.data, lvl.ctypes.data, vc.ctypes.data, ok.ctypes.data)
     return iz, u, v, lvl, vc, ok
+
+
+GRID_COLS, GRID_ROWS, HISTO_LENGTH = 64, 48, 30
+
+
+def assign_features_to_grid(x, y, min_x, max_x, min_y, max_y):
+    """Frame::AssignFeaturesToGrid as CSR: (cell_start[64*48+1], cell_items[n]); cell = ix*48+iy."""
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    winv = np.float32(GRID_COLS) / (np.float32(max_x) - np.float32(min_x))
+    hinv = np.float32(GRID_ROWS) / (np.float32(max_y) - np.float32(min_y))
+    start = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+    items = np.full(max(len(x), 1), -1, np.int32)
+    lib().orc_assign_features_to_grid(len(x), x.ctypes.data, y.ctypes.data, min_x, min_y, winv, hinv, start.ctypes.data, items.ctypes.data)
+    return start, items[:start[-1]]
+
+
+def search_by_projection(last, cur, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_y, max_y, mbf, th, scale_factors, level_mode,
+                         th_high=100, check_orientation=True):
+    """last: dict(P[3,n], octave, angle, desc[n,32]); cur: dict(x, y, octave, angle, uright, occupied, desc[m,32]).
+    -> dict(nmatches, best_idx2, best_dist, rot_bin, cur_match, hist)."""
+    a = lambda v, t: np.ascontiguousarray(v, t)
+    P = a(last["P"], np.float32); lo = a(last["octave"], np.int32); la = a(last["angle"], np.float32); ld = a(last["desc"], np.uint8)
+    cxs = a(cur["x"], np.float32); cys = a(cur["y"], np.float32); co = a(cur["octave"], np.int32); ca = a(cur["angle"], np.float32)
+    cu = a(cur["uright"], np.float32); occ = a(cur["occupied"], np.uint8); cd = a(cur["desc"], np.uint8)
+    Rcw = a(Rcw, np.float32); tcw = a(tcw, np.float32); sf = a(scale_factors, np.float32)
+    n, m = P.shape[1], len(cxs)
+    bi = np.zeros(max(n, 1), np.int32); bd = np.zeros(max(n, 1), np.int32); rb = np.zeros(max(n, 1), np.int32)
+    cm = np.zeros(max(m, 1), np.int32); hist = np.zeros(HISTO_LENGTH, np.int32)
+    nm = lib().orc_search_by_projection(n, P[0].ctypes.data, P[1].ctypes.data, P[2].ctypes.data, lo.ctypes.data, la.ctypes.data,
+                                        ld.ctypes.data, Rcw.ctypes.data, tcw.ctypes.data, fx, fy, cx, cy, min_x, max_x, min_y, max_y,
+                                        mbf, th, sf.ctypes.data, level_mode, m, cxs.ctypes.data, cys.ctypes.data, co.ctypes.data,
+                                        ca.ctypes.data, cu.ctypes.data, occ.ctypes.data, cd.ctypes.data, th_high,
+                                        int(check_orientation), bi.ctypes.data, bd.ctypes.data, rb.ctypes.data, cm.ctypes.data,
+                                        hist.ctypes.data)
+    return dict(nmatches=nm, best_idx2=bi[:n], best_dist=bd[:n], rot_bin=rb[:n], cur_match=cm[:m], hist=hist)
