@@ -167,23 +167,38 @@ def cpu_pairs_per_s(cfg, pairs_imgs, threads, pairs_total):
     return pairs_total / dt, dt
 
 
-def ref_cuda_pairs_per_s(cfg, pair, iters=40):
-    """The reference's own src/cuda (compiled unmodified for sm_100a, oracle/_ref) driven like Frame::Frame does."""
+def _ref_cuda_inproc(cfg, pair, iters=40):
+    from oracle import ref
+    if not ref.available():
+        return None
+    kw = cfg.extractor_kwargs()
+    rl, rr = ref.RefEye(**kw), ref.RefEye(**kw)
+    ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, 10, True)
+    out = {}
+    for two in (True, False):
+        dt = ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, iters, two)
+        out["two_threads" if two else "one_thread"] = iters / dt
+    rl.close()
+    rr.close()
+    return {"value": max(out.values()), "unit": UNIT, "detail": out, "iters": iters,
+            "how": "ORB_GPU::extract x2 (host images, its own H2D/D2H) + ORB_compute_stereo_match, wall clock, in a fresh process"}
+
+
+def ref_cuda_pairs_per_s(cfg, seed=0, iters=40):
+    """The reference's own src/cuda (compiled unmodified for sm_100a, oracle/_ref) driven like Frame::Frame does.  Run in a
+    fresh interpreter without torch: the reference allocates, frees and creates a cuBLAS handle per frame, and those driver
+    calls were measured 4-10x slower inside a process that already holds a torch CUDA context and this library's arenas."""
+    import subprocess
+    key = [k for k, v in __import__("jetson_slam_b200.configs", fromlist=["CONFIGS"]).CONFIGS.items() if v is cfg][0]
+    code = ("import json,sys; sys.path.insert(0, %r); import bench; from jetson_slam_b200 import synth; from jetson_slam_b200.configs import CONFIGS; "
+            "cfg = CONFIGS[%r]; print(json.dumps(bench._ref_cuda_inproc(cfg, synth.stereo_pair(cfg.height, cfg.width, %d), %d)))"
+            % (ROOT, key, seed, iters))
     try:
-        from oracle import ref
-        if not ref.available():
-            return None
-        kw = cfg.extractor_kwargs()
-        rl, rr = ref.RefEye(**kw), ref.RefEye(**kw)
-        ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, 5, True)
-        out = {}
-        for two in (True, False):
-            dt = ref.time_pairs(rl, rr, pair[0], pair[1], cfg.mb, cfg.mbf, iters, two)
-            out["two_threads" if two else "one_thread"] = iters / dt
-        rl.close()
-        rr.close()
-        return {"value": max(out.values()), "unit": UNIT, "detail": out, "iters": iters,
-                "how": "ORB_GPU::extract x2 (host images, its own H2D/D2H) + ORB_compute_stereo_match, wall clock"}
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        last = [l for l in r.stdout.strip().splitlines() if l.startswith("{") or l == "null"]
+        if r.returncode != 0 or not last:
+            return {"unavailable": (r.stderr or r.stdout)[-200:]}
+        return json.loads(last[-1])
     except Exception as e:  # the reference library is optional colour, never the measured product
         return {"unavailable": repr(e)[:200]}
 
@@ -252,7 +267,7 @@ def run_reference_arm(args, cfg):
     try:
         import torch
         if torch.cuda.is_available():
-            line["ref_cuda"] = ref_cuda_pairs_per_s(cfg, imgs[0])
+            line["ref_cuda"] = ref_cuda_pairs_per_s(cfg)
     except Exception:
         pass
     print(json.dumps(line), flush=True)
@@ -292,7 +307,7 @@ def run_ours(args, cfg):
     pairs = [synth.stereo_pair(cfg.height, cfg.width, 1000 * rank + s) for s in range(n_distinct)]
     # colour only: the reference's own src/cuda on this GPU, timed before this process owns any device memory of ours
     # (it allocates and frees per frame, which gets slower the more the process has mapped)
-    ref_cuda = ref_cuda_pairs_per_s(cfg, pairs[0]) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
+    ref_cuda = ref_cuda_pairs_per_s(cfg, 1000 * rank) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
     fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
     host = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
