@@ -100,6 +100,11 @@ struct jsfe_handle {
     uint8_t* d_stage = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;
+    // single-chunk calls of jsfe_process_host_pairs replay one CUDA graph (re-pitch + kernels + D2H); key = what is baked in
+    cudaGraphExec_t pair_graph = nullptr;
+    int pg_pairs = 0, pg_th_high = 0, pg_th_low = 0;
+    float pg_mb = 0.f, pg_mbf = 0.f;
+    bool pg_disabled = false;
 };
 
 namespace {
@@ -519,6 +524,7 @@ int jsfe_destroy(jsfe_handle* h) {
     if (h->st_aux) cudaStreamDestroy(h->st_aux);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
     if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
     if (h->st_comp) cudaStreamDestroy(h->st_comp);
     if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
@@ -875,7 +881,47 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
     const size_t cap = P.cap;
     const bool saved_prof = h->profiling;
     h->profiling = false;
-    for (int c = 0, p0 = 0; c < n_chunks; p0 += sizes[c], ++c) {
+    auto enqueue_results = [&](int s0, int ns, cudaStream_t st) -> int {
+        CU(cudaMemcpyAsync(h->h_n + s0, P.n_kp + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_kps + (size_t)s0 * 6 * cap, P.kps + (size_t)s0 * 6 * cap, (size_t)ns * 6 * cap * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_desc + (size_t)s0 * cap * 32, P.desc + (size_t)s0 * cap * 32, (size_t)ns * cap * 32, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_ur + (size_t)s0 * cap, P.u_right + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->h_dp + (size_t)s0 * cap, P.depth + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, st));
+        return JSFE_OK;
+    };
+    bool done_by_graph = false;
+    if (n_chunks == 1 && !h->pg_disabled && !getenv("JSFE_NO_GRAPH")) {
+        // latency path (one frame at a time): everything after the upload is one graph launch
+        const bool hit = h->pair_graph && h->pg_pairs == n_pairs && h->pg_th_high == th_high && h->pg_th_low == th_low &&
+                         h->pg_mb == mb && h->pg_mbf == mbf;
+        if (!hit) {
+            if (h->pair_graph) { cudaGraphExecDestroy(h->pair_graph); h->pair_graph = nullptr; }
+            cudaGraph_t g_cap = nullptr;
+            bool ok = cudaStreamBeginCapture(h->st_comp, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = jsfe_set_images(h, 0, 2 * n_pairs, h->d_stage, g.w, (int64_t)img_bytes, 1, h->st_comp) == JSFE_OK &&
+                     jsfe_extract(h, 0, 2 * n_pairs, h->st_comp) == JSFE_OK &&
+                     jsfe_stereo_match(h, 0, n_pairs, th_high, th_low, mb, mbf, h->st_comp) == JSFE_OK &&
+                     enqueue_results(0, 2 * n_pairs, h->st_comp) == JSFE_OK;
+                ok = (cudaStreamEndCapture(h->st_comp, &g_cap) == cudaSuccess) && ok && g_cap;
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->pair_graph, g_cap, 0) == cudaSuccess;
+            if (g_cap) cudaGraphDestroy(g_cap);
+            if (!ok) {   // capture is an optimisation: fall back to stream launches for good
+                cudaGetLastError();
+                h->pair_graph = nullptr;
+                h->pg_disabled = true;
+            } else {
+                h->pg_pairs = n_pairs; h->pg_th_high = th_high; h->pg_th_low = th_low; h->pg_mb = mb; h->pg_mbf = mbf;
+            }
+        }
+        if (h->pair_graph) {
+            CU(cudaMemcpyAsync(h->d_stage, images, img_bytes * 2 * n_pairs, cudaMemcpyHostToDevice, h->st_comp));
+            CU(cudaGraphLaunch(h->pair_graph, h->st_comp));
+            done_by_graph = true;
+        }
+    }
+    for (int c = 0, p0 = 0; c < n_chunks && !done_by_graph; p0 += sizes[c], ++c) {
         const int np = sizes[c];
         const int s0 = 2 * p0, ns = 2 * np;
         // 1. one contiguous H2D per chunk (2-D copies with odd row widths run far below PCIe speed)
@@ -889,11 +935,7 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
         CU(cudaEventRecord(h->ev_done[c], h->st_comp));
         // 3. results of this chunk back to pinned host memory while the next chunk computes
         CU(cudaStreamWaitEvent(h->st_d2h, h->ev_done[c], 0));
-        CU(cudaMemcpyAsync(h->h_n + s0, P.n_kp + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(cudaMemcpyAsync(h->h_kps + (size_t)s0 * 6 * cap, P.kps + (size_t)s0 * 6 * cap, (size_t)ns * 6 * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(cudaMemcpyAsync(h->h_desc + (size_t)s0 * cap * 32, P.desc + (size_t)s0 * cap * 32, (size_t)ns * cap * 32, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(cudaMemcpyAsync(h->h_ur + (size_t)s0 * cap, P.u_right + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
-        CU(cudaMemcpyAsync(h->h_dp + (size_t)s0 * cap, P.depth + (size_t)s0 * cap, (size_t)ns * cap * 4, cudaMemcpyDeviceToHost, h->st_d2h));
+        if ((rc = enqueue_results(s0, ns, h->st_d2h))) break;
     }
     h->profiling = saved_prof;
     cudaError_t e1 = cudaStreamSynchronize(h->st_h2d), e2 = cudaStreamSynchronize(h->st_comp), e3 = cudaStreamSynchronize(h->st_d2h);
