@@ -234,6 +234,35 @@ def sbp_microbench(iters=200):
             "device-resident inputs, CUDA events over %d calls; CPU = oracle restatement of the host loops, 1 thread" % iters}
 
 
+def remap_microbench(n_images=64, iters=50):
+    """SURVEY.md 8(f3): device rectification (cv::remap INTER_LINEAR semantics) of a batch of EuRoC-size frames sharing one
+    map pair.  Algorithmic bytes per launch: n * (src h*w read + dst h*w write) + 8 B/px of maps once."""
+    import torch
+    from jetson_slam_b200 import frontend
+    h, w = 480, 752
+    rng = np.random.default_rng(5)
+    xs, ys = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    r2 = ((xs - w / 2) ** 2 + (ys - h / 2) ** 2) / np.float32(w * w)
+    mx = torch.from_numpy((xs + (xs - w / 2) * 0.1 * r2 + 0.37).astype(np.float32)).cuda()
+    my = torch.from_numpy((ys + (ys - h / 2) * 0.1 * r2 - 0.21).astype(np.float32)).cuda()
+    src = torch.from_numpy(rng.integers(0, 256, size=(n_images, h, w), dtype=np.uint8)).cuda()
+    out = torch.empty_like(src)
+    for _ in range(5):
+        frontend.remap_bilinear(src, mx, my, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        frontend.remap_bilinear(src, mx, my, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = n_images * 2 * h * w + 8 * h * w
+    peak, _ = measured_hbm_peak()
+    return {"images": n_images, "height": h, "width": w, "ms_per_launch": ms, "us_per_image": ms * 1e3 / n_images,
+            "alg_bytes_per_launch": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -520,7 +549,7 @@ def run_ours(args, cfg):
             line["ref_cuda"] = ref_cuda
         if world == 1:
             try:
-                line["adjacent"] = {"search_by_projection": sbp_microbench()}
+                line["adjacent"] = {"search_by_projection": sbp_microbench(), "remap_bilinear": remap_microbench()}
             except Exception as e:   # adjacent-row colour must never break the headline line
                 line["adjacent"] = {"search_by_projection": {"error": repr(e)[:200]}}
         print(json.dumps(line), flush=True)

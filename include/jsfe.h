@@ -234,6 +234,20 @@ typedef struct jsfe_sbp_args {
 } jsfe_sbp_args;
 int jsfe_search_by_projection(const jsfe_sbp_args* args, void* stream);
 
+/* ---- the input side on the device.  DEVICE pointers, enqueued on `stream`, not synchronised.
+ * jsfe_remap_bilinear replaces cv::remap(im, rect, M1, M2, cv::INTER_LINEAR) of the reference's stereo examples
+ * (Examples/Stereo/stereo_euroc.cpp:106-107,145-146): 8-bit single channel, CV_32FC1 maps [dst_h][dst_w] (contiguous) as
+ * cv::initUndistortRectifyMap(..., CV_32F, ...) returns them, BORDER_CONSTANT 0, OpenCV's fixed-point bilinear scheme
+ * (bit-exact with OpenCV 4.x).  `n_images` source images `src_stride` bytes apart share the maps (frames of one camera);
+ * image i is written at dst + i*dst_stride -- e.g. straight into the level-0 slots (jsfe_slot_image) of every second slot.
+ * jsfe_cvt_gray replaces cv::cvtColor(im, im, CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY | CV_BGRA2GRAY) of
+ * Tracking::GrabImageStereo (src/Tracking.cpp:260-285): channels = 3 or 4 interleaved, rgb_order != 0 for RGB(A). */
+int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pitch, int64_t src_stride, int n_images,
+                        const float* map_x, const float* map_y, int dst_h, int dst_w, uint8_t* dst, int64_t dst_pitch,
+                        int64_t dst_stride, void* stream);
+int jsfe_cvt_gray(const uint8_t* src, int h, int w, int64_t src_pitch, int channels, int rgb_order, uint8_t* dst, int64_t dst_pitch,
+                  void* stream);
+
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);
 /* the 7x7-blurred level (descriptor input); zero outside [20,h-20)x[20,w-20) like the reference's image_gaussian_ */

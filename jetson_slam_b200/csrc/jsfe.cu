@@ -1030,6 +1030,34 @@ int jsfe_search_by_projection(const jsfe_sbp_args* a, void* stream) {
     return JSFE_OK;
 }
 
+int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pitch, int64_t src_stride, int n_images,
+                        const float* map_x, const float* map_y, int dst_h, int dst_w, uint8_t* dst, int64_t dst_pitch,
+                        int64_t dst_stride, void* stream) {
+    if (!src || !map_x || !map_y || !dst || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1 || src_pitch < src_w || dst_pitch < dst_w ||
+        n_images < 0 || src_h > 32767 || src_w > 32767)
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n_images == 0) return JSFE_OK;
+    const int word_stores = ((uintptr_t)dst % 4 == 0) && (dst_pitch % 4 == 0) && (dst_stride % 4 == 0);
+    // images in flight per output tile: enough blocks to fill the GPU, few enough that the decoded maps are reused
+    const int tiles = ((dst_w + 255) / 256) * ((dst_h + 3) / 4);
+    const int gz = std::max(1, std::min(n_images, (148 * 8 + tiles - 1) / tiles));
+    jsfe::k_remap_bilinear<<<dim3((dst_w + 255) / 256, (dst_h + 3) / 4, gz), 256, 0, (cudaStream_t)stream>>>(
+        src, src_h, src_w, (long long)src_pitch, (long long)src_stride, n_images, map_x, map_y, dst_h, dst_w, dst, (long long)dst_pitch,
+        (long long)dst_stride, word_stores);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
+int jsfe_cvt_gray(const uint8_t* src, int h, int w, int64_t src_pitch, int channels, int rgb_order, uint8_t* dst, int64_t dst_pitch,
+                  void* stream) {
+    if (!src || !dst || h < 1 || w < 1 || (channels != 3 && channels != 4) || src_pitch < (int64_t)w * channels || dst_pitch < w || h > 65535)
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    jsfe::k_cvt_gray<<<dim3((w + 255) / 256, h), 256, 0, (cudaStream_t)stream>>>(src, h, w, (long long)src_pitch, channels,
+                                                                               rgb_order ? 2 : 0, dst, (long long)dst_pitch);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst) {
     int rc = check_slots(h, slot, 1);
     if (rc) return rc;

@@ -1313,6 +1313,71 @@ __global__ void __launch_bounds__(1024) k_sbp_finish(const __grid_constant__ Sbp
     if (threadIdx.x == 0) *a.n_matches -= s_culled;
 }
 
+// =================================================================================================
+// the input side on the device, so a raw camera frame crosses PCIe once.
+//   k_remap_bilinear  cv::remap(src, dst, map_x, map_y, INTER_LINEAR), CV_32FC1 maps, BORDER_CONSTANT 0, 8-bit, as the
+//                     reference's stereo example rectifies (Examples/Stereo/stereo_euroc.cpp:106-107,145-146); OpenCV's
+//                     fixed-point scheme: coordinates rounded to 1/32 px, int16 weights scaled by 2^15 (imgwarp.cpp).
+//                     Thread = 4 output pixels of one row; the decoded map entry (tap address, 4 weights) is reused for
+//                     every image of the batch (frames of one camera share the maps), so the 8 B/px of map traffic is
+//                     paid once per batch and each image costs ~1 B read (L2-gathered taps) + 1 B write per pixel.
+//   k_cvt_gray        cv::cvtColor(*2GRAY) for 8-bit BGR/RGB(A) (src/Tracking.cpp:260-285): 15-bit coefficients.
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_remap_bilinear(const uint8_t* __restrict__ src, int src_h, int src_w, long long src_pitch,
+                                                        long long src_stride, int n_images, const float* __restrict__ map_x,
+                                                        const float* __restrict__ map_y, int dst_h, int dst_w,
+                                                        uint8_t* __restrict__ dst, long long dst_pitch, long long dst_stride,
+                                                        int word_stores) {
+    const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) << 2, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x4 >= dst_w || y >= dst_h) return;
+    long long off[4];      // offset of tap (iy, ix) in the source image (may point outside: guarded by the valid bits)
+    unsigned w01[4], w23[4];   // packed int16 weights: (w00 | w01 << 16), (w10 | w11 << 16)
+    unsigned valid = 0;    // 4 bits per pixel: tap k of pixel j inside the source
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        off[j] = 0; w01[j] = 0; w23[j] = 0;
+        if (x4 + j < dst_w) {
+            const size_t m = (size_t)y * dst_w + x4 + j;
+            const int sx = __float2int_rn(__fmul_rn(__ldg(map_x + m), 32.0f)), sy = __float2int_rn(__fmul_rn(__ldg(map_y + m), 32.0f));
+            const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767), fx = sx & 31, fy = sy & 31;
+            int a = (32 - fx) * (32 - fy) * 32, b = fx * (32 - fy) * 32, c = (32 - fx) * fy * 32, d = fx * fy * 32;
+            if ((fx | fy) == 0) { a = 32767; d = 1; }     // BilinearTab_i[0]: 32768 saturates to short, the 1 goes to tap (1,1)
+            w01[j] = (unsigned)a | ((unsigned)b << 16);
+            w23[j] = (unsigned)c | ((unsigned)d << 16);
+            off[j] = (long long)iy * src_pitch + ix;
+            const unsigned x0 = (unsigned)ix < (unsigned)src_w, x1 = (unsigned)(ix + 1) < (unsigned)src_w;
+            const unsigned y0 = (unsigned)iy < (unsigned)src_h, y1 = (unsigned)(iy + 1) < (unsigned)src_h;
+            valid |= ((x0 & y0) | ((x1 & y0) << 1) | ((x0 & y1) << 2) | ((x1 & y1) << 3)) << (4 * j);
+        }
+    }
+    for (int img = blockIdx.z; img < n_images; img += gridDim.z) {
+        const uint8_t* __restrict__ s = src + (size_t)img * src_stride;
+        unsigned out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* p = s + off[j];
+            const unsigned vb = valid >> (4 * j);
+            const int v0 = (vb & 1u) ? (int)__ldg(p) : 0, v1 = (vb & 2u) ? (int)__ldg(p + 1) : 0;
+            const int v2 = (vb & 4u) ? (int)__ldg(p + src_pitch) : 0, v3 = (vb & 8u) ? (int)__ldg(p + src_pitch + 1) : 0;
+            const int acc = v0 * (int)(w01[j] & 0xFFFFu) + v1 * (int)(w01[j] >> 16) + v2 * (int)(w23[j] & 0xFFFFu) + v3 * (int)(w23[j] >> 16);
+            out |= (unsigned)min((acc + (1 << 14)) >> 15, 255) << (8 * j);
+        }
+        uint8_t* o = dst + (size_t)img * dst_stride + (size_t)y * dst_pitch + x4;
+        if (word_stores && x4 + 3 < dst_w) *reinterpret_cast<unsigned*>(o) = out;
+        else
+            for (int j = 0; j < 4 && x4 + j < dst_w; ++j) o[j] = (uint8_t)(out >> (8 * j));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cvt_gray(const uint8_t* __restrict__ src, int h, int w, long long src_pitch, int channels,
+                                                  int blue_idx, uint8_t* __restrict__ dst, long long dst_pitch) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* p = src + (size_t)y * src_pitch + (size_t)x * channels;
+    const int b = p[blue_idx], g = p[1], r = p[blue_idx ^ 2];
+    dst[(size_t)y * dst_pitch + x] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+}
+
 __global__ void __launch_bounds__(256) k_hamming_pairs(int n, const int* __restrict__ idx_l, const int* __restrict__ idx_r,
                                                        const uint8_t* __restrict__ desc_l, const uint8_t* __restrict__ desc_r,
                                                        int* __restrict__ dist) {

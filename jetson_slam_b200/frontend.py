@@ -86,6 +86,9 @@ def lib():
         L.jsfe_in_frustum.argtypes = [C.c_int] + [vp] * 12 + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
         L.jsfe_build_frame_grid.argtypes = [C.c_int, vp, vp, f, f, f, f, vp, vp, vp]
         L.jsfe_search_by_projection.argtypes = [vp, vp]
+        i64 = C.c_int64
+        L.jsfe_remap_bilinear.argtypes = [vp, C.c_int, C.c_int, i64, i64, C.c_int, vp, vp, C.c_int, C.c_int, vp, i64, i64, vp]
+        L.jsfe_cvt_gray.argtypes = [vp, C.c_int, C.c_int, i64, C.c_int, C.c_int, vp, i64, vp]
         L.jsfe_debug_level_image.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_level_blur.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_debug_cells.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -423,4 +426,34 @@ def search_by_projection(last, cur, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_
     _check(lib().jsfe_search_by_projection(C.byref(a), _stream_ptr(stream)))
     out["best_idx2"], out["best_dist"], out["rot_bin"], out["cur_match"] = out["best_idx2"][:n], out["best_dist"][:n], out["rot_bin"][:n], out["cur_match"][:m]
     out["grid"] = grid
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- SURVEY 8(f3)
+def remap_bilinear(src, map_x, map_y, out=None, stream=None):
+    """Device cv::remap(src, map_x, map_y, INTER_LINEAR) (Examples/Stereo/stereo_euroc.cpp:145-146), bit-exact with OpenCV 4.x.
+    src: u8 CUDA tensor [n, h, w] (or [h, w]); map_x, map_y: contiguous f32 CUDA tensors [H, W] shared by the n images.
+    out: optional u8 CUDA tensor [n, H, W'] view to write into (row/image strides are taken from it). -> out."""
+    import torch
+    one = src.dim() == 2
+    s3 = src.unsqueeze(0) if one else src
+    assert s3.stride(2) == 1 and map_x.is_contiguous() and map_y.is_contiguous() and map_x.shape == map_y.shape
+    n, h, w = s3.shape
+    H, W = map_x.shape
+    if out is None:
+        out = torch.empty((n, H, W), dtype=torch.uint8, device=src.device)
+    o3 = out.unsqueeze(0) if out.dim() == 2 else out
+    assert o3.stride(2) == 1 and o3.shape[0] == n and o3.shape[1] == H and o3.shape[2] >= W
+    _check(lib().jsfe_remap_bilinear(_ptr(s3), h, w, s3.stride(1), s3.stride(0) if n > 1 else h * s3.stride(1), n, _ptr(map_x), _ptr(map_y),
+                                     H, W, _ptr(o3), o3.stride(1), o3.stride(0) if n > 1 else H * o3.stride(1), _stream_ptr(stream)))
+    return out[0] if (one and out.dim() == 3) else out
+
+
+def cvt_gray(img, rgb=False, stream=None):
+    """Device cv::cvtColor(img, *2GRAY) (src/Tracking.cpp:260-285): img u8 CUDA tensor [h, w, 3|4] contiguous -> [h, w]."""
+    import torch
+    assert img.is_contiguous() and img.shape[2] in (3, 4)
+    h, w, c = img.shape
+    out = torch.empty((h, w), dtype=torch.uint8, device=img.device)
+    _check(lib().jsfe_cvt_gray(_ptr(img), h, w, w * c, c, int(bool(rgb)), _ptr(out), w, _stream_ptr(stream)))
     return out

@@ -160,6 +160,13 @@ int orc_search_by_projection(int n_last, const float* px, const float* py, const
                              int check_orientation, int32_t* best_idx2, int32_t* best_dist, int32_t* rot_bin,
                              int32_t* cur_match, int32_t* hist /* 30 */);
 
+/* ---- cv::remap(INTER_LINEAR, CV_32FC1 maps, BORDER_CONSTANT 0) and cv::cvtColor(*2GRAY) for 8-bit images
+ * (Examples/Stereo/stereo_euroc.cpp:106-107,145-146; src/Tracking.cpp:260-285).  OpenCV's published algorithm, PINNED
+ * bit-exactly against the cv2 4.13 wheel of this image. */
+void orc_remap_bilinear_u8(const uint8_t* src, int src_h, int src_w, int64_t src_pitch, const float* map_x, const float* map_y,
+                           int dst_h, int dst_w, uint8_t* dst, int64_t dst_pitch);
+void orc_cvt_gray_u8(const uint8_t* src, int64_t n_pixels, int channels, int blue_idx, uint8_t* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ def lib():
         L.orc_project_points.argtypes = [ci] + [vpp] * 5 + [f] * 8 + [vpp] * 4
         L.orc_hamming_pairs.argtypes = [ci] + [vpp] * 5
         L.orc_in_frustum.argtypes = [ci] + [vpp] * 12 + [f] * 4 + [ci] * 5 + [f] * 2 + [vpp] * 6
+        L.orc_remap_bilinear_u8.argtypes = [vpp, ci, ci, C.c_int64, vpp, vpp, ci, ci, vpp, C.c_int64]
+        L.orc_cvt_gray_u8.argtypes = [vpp, C.c_int64, ci, ci, vpp]
         L.orc_assign_features_to_grid.argtypes = [ci, vpp, vpp, f, f, f, f, vpp, vpp]
         L.orc_search_by_projection.restype = ci
         L.orc_search_by_projection.argtypes = [ci] + [vpp] * 8 + [f] * 10 + [vpp, ci, ci] + [vpp] * 7 + [ci, ci] + [vpp] * 5
@@ -256,3 +258,20 @@ def search_by_projection(last, cur, Rcw, tcw, fx, fy, cx, cy, min_x, max_x, min_
                                         int(check_orientation), bi.ctypes.data, bd.ctypes.data, rb.ctypes.data, cm.ctypes.data,
                                         hist.ctypes.data)
     return dict(nmatches=nm, best_idx2=bi[:n], best_dist=bd[:n], rot_bin=rb[:n], cur_match=cm[:m], hist=hist)
+
+
+def remap_bilinear(src, map_x, map_y):
+    """cv::remap(src, map_x, map_y, INTER_LINEAR) for one 8-bit channel (BORDER_CONSTANT 0)."""
+    src = np.ascontiguousarray(src, np.uint8); mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
+    dst = np.zeros(mx.shape, np.uint8)
+    lib().orc_remap_bilinear_u8(src.ctypes.data, src.shape[0], src.shape[1], src.shape[1], mx.ctypes.data, my.ctypes.data,
+                                mx.shape[0], mx.shape[1], dst.ctypes.data, mx.shape[1])
+    return dst
+
+
+def cvt_gray(img, rgb=False):
+    """cv::cvtColor(img, BGR2GRAY / RGB2GRAY / BGRA2GRAY / RGBA2GRAY) for 8-bit interleaved images [h, w, 3|4]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    dst = np.zeros(img.shape[:2], np.uint8)
+    lib().orc_cvt_gray_u8(img.ctypes.data, img.shape[0] * img.shape[1], img.shape[2], 2 if rgb else 0, dst.ctypes.data)
+    return dst
