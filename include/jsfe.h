@@ -234,6 +234,20 @@ typedef struct jsfe_sbp_args {
 } jsfe_sbp_args;
 int jsfe_search_by_projection(const jsfe_sbp_args* args, void* stream);
 
+/* ---- the output side on the device.  Frame::Frame unpacks the 6-plane SoA into
+ * std::vector<cv::KeyPoint> on the host, one field at a time (src/Frame.cpp:116-196: pt.x/pt.y = int -> float, response =
+ * score, angle in degrees, octave, size).  jsfe_frame_view does that unpack on the device for slot `slot`:
+ *   keys  : [capacity] records with cv::KeyPoint's memory layout (pt.x, pt.y, size, angle, response, octave, class_id = -1),
+ *           so ONE device->host copy of n*28 bytes fills mvKeys' storage;
+ *   x, y, angle (f32), octave (i32): [capacity] planes = the mvKeysUn arrays jsfe_build_frame_grid / jsfe_search_by_projection
+ *           read, so the tracking-thread searches run on extractor output without a host round trip.
+ * Any output pointer may be NULL.  Device pointers; the first n_keypoints entries are valid.  Not synchronised. */
+typedef struct jsfe_cv_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} jsfe_cv_keypoint;
+int jsfe_frame_view(jsfe_handle* h, int slot, jsfe_cv_keypoint* keys, float* x, float* y, int32_t* octave, float* angle, void* stream);
+
 /* ---- the input side on the device.  DEVICE pointers, enqueued on `stream`, not synchronised.
  * jsfe_remap_bilinear replaces cv::remap(im, rect, M1, M2, cv::INTER_LINEAR) of the reference's stereo examples
  * (Examples/Stereo/stereo_euroc.cpp:106-107,145-146): 8-bit single channel, CV_32FC1 maps [dst_h][dst_w] (contiguous) as

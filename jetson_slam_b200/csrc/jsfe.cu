@@ -1030,6 +1030,15 @@ int jsfe_search_by_projection(const jsfe_sbp_args* a, void* stream) {
     return JSFE_OK;
 }
 
+int jsfe_frame_view(jsfe_handle* h, int slot, jsfe_cv_keypoint* keys, float* x, float* y, int32_t* octave, float* angle, void* stream) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    jsfe::k_frame_view<<<(h->P.cap + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P, slot, keys, x, y, octave, angle);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
 int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pitch, int64_t src_stride, int n_images,
                         const float* map_x, const float* map_y, int dst_h, int dst_w, uint8_t* dst, int64_t dst_pitch,
                         int64_t dst_stride, void* stream) {

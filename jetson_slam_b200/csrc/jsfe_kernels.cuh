@@ -1313,6 +1313,27 @@ __global__ void __launch_bounds__(1024) k_sbp_finish(const __grid_constant__ Sbp
     if (threadIdx.x == 0) *a.n_matches -= s_culled;
 }
 
+// Frame::Frame's SoA -> cv::KeyPoint unpack (src/Frame.cpp:116-196) on the device
+__global__ void __launch_bounds__(256) k_frame_view(const __grid_constant__ Params p, int slot, ::jsfe_cv_keypoint* __restrict__ keys,
+                                                    float* __restrict__ x, float* __restrict__ y, int* __restrict__ octave,
+                                                    float* __restrict__ angle) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_kp[slot]) return;
+    const int* kp = p.kps + (size_t)slot * 6 * p.cap;
+    const float fx = (float)kp[i], fy = (float)kp[p.cap + i], ang = __int_as_float(kp[3 * p.cap + i]);
+    const int oct = kp[4 * p.cap + i];
+    if (keys) {
+        ::jsfe_cv_keypoint k;
+        k.x = fx; k.y = fy; k.size = (float)kp[5 * p.cap + i]; k.angle = ang; k.response = (float)kp[2 * p.cap + i];
+        k.octave = oct; k.class_id = -1;
+        keys[i] = k;
+    }
+    if (x) x[i] = fx;
+    if (y) y[i] = fy;
+    if (octave) octave[i] = oct;
+    if (angle) angle[i] = ang;
+}
+
 // =================================================================================================
 // the input side on the device, so a raw camera frame crosses PCIe once.
 //   k_remap_bilinear  cv::remap(src, dst, map_x, map_y, INTER_LINEAR), CV_32FC1 maps, BORDER_CONSTANT 0, 8-bit, as the

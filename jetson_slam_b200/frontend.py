@@ -86,6 +86,7 @@ def lib():
         L.jsfe_in_frustum.argtypes = [C.c_int] + [vp] * 12 + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
         L.jsfe_build_frame_grid.argtypes = [C.c_int, vp, vp, f, f, f, f, vp, vp, vp]
         L.jsfe_search_by_projection.argtypes = [vp, vp]
+        L.jsfe_frame_view.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
         i64 = C.c_int64
         L.jsfe_remap_bilinear.argtypes = [vp, C.c_int, C.c_int, i64, i64, C.c_int, vp, vp, C.c_int, C.c_int, vp, i64, i64, vp]
         L.jsfe_cvt_gray.argtypes = [vp, C.c_int, C.c_int, i64, C.c_int, C.c_int, vp, i64, vp]
@@ -457,3 +458,32 @@ def cvt_gray(img, rgb=False, stream=None):
     out = torch.empty((h, w), dtype=torch.uint8, device=img.device)
     _check(lib().jsfe_cvt_gray(_ptr(img), h, w, w * c, c, int(bool(rgb)), _ptr(out), w, _stream_ptr(stream)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- SURVEY 8(f4)
+CV_KEYPOINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32), ("angle", np.float32),
+                              ("response", np.float32), ("octave", np.int32), ("class_id", np.int32)])   # cv::KeyPoint, 28 bytes
+
+
+def frame_view(fe, slot, stream=None):
+    """Device Frame::Frame unpack (src/Frame.cpp:116-196) of slot `slot` of Frontend `fe`.
+    -> dict of CUDA tensors: keys u8 [cap, 28] (cv::KeyPoint records), x, y, angle f32 [cap], octave i32 [cap]; valid: first n."""
+    import torch
+    dev = torch.device("cuda", fe.device)
+    cap = fe.max_kp
+    out = dict(keys=torch.zeros((cap, 28), dtype=torch.uint8, device=dev), x=torch.zeros(cap, dtype=torch.float32, device=dev),
+               y=torch.zeros(cap, dtype=torch.float32, device=dev), octave=torch.zeros(cap, dtype=torch.int32, device=dev),
+               angle=torch.zeros(cap, dtype=torch.float32, device=dev))
+    _check(lib().jsfe_frame_view(fe._h, slot, _ptr(out["keys"]), _ptr(out["x"]), _ptr(out["y"]), _ptr(out["octave"]), _ptr(out["angle"]),
+                                 _stream_ptr(stream)))
+    return out
+
+
+class DevicePtr:
+    """A raw device pointer owned by a handle (e.g. a jsfe_slot_view field), usable wherever the bindings take a CUDA tensor."""
+
+    def __init__(self, ptr):
+        self._p = int(ptr or 0)
+
+    def data_ptr(self):
+        return self._p

@@ -238,3 +238,58 @@ def test_cuda_ties_clusters_and_degenerate_inputs():
     empty_last = dict(P=np.zeros((3, 0), F), octave=np.zeros(0, np.int32), angle=np.zeros(0, F), desc=np.zeros((0, 32), np.uint8))
     got = run_cuda(empty_last, cur, R, t, 7.0, 0)
     assert got["nmatches"] == 0 and (got["cur_match"] == -1).all()
+
+
+@pytest.mark.gpu
+def test_device_resident_chain_extract_stereo_view_grid_search():
+    """Rows a12 / f1 / f4 end to end on the device: extract two stereo frames, stereo-match, unpack the current frame with
+    jsfe_frame_view, and run the fused SearchByProjection on those device arrays (uRight and descriptors straight from the slot
+    view) -- then check against the oracle fed with host copies of the same arrays."""
+    import torch
+    from jetson_slam_b200 import frontend
+    from jetson_slam_b200.configs import CONFIGS
+    cfg = CONFIGS["C1"]
+    h, w = cfg.height, cfg.width
+    la, ra = synth.stereo_pair(h, w, 77)
+    shift = lambda im: np.roll(im, (1, 3), axis=(0, 1))      # the "current" frame: the same scene moved by (3, 1) pixels
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=4)
+    fe.set_images(np.stack([la, ra, shift(la), shift(ra)]))
+    fe.extract(0, 4)
+    fe.stereo_match(cfg.mb, cfg.mbf, 0, 2)
+    torch.cuda.synchronize()
+    # last frame (pair 0) on the host: keypoints with depth become map points (that is SLAM-core work, done on the CPU)
+    kA, dA = fe.get_keypoints(0)
+    urA, depA, _, _ = fe.get_stereo(0)
+    good = depA > 0
+    fx = fy = cfg.fx
+    cx, cy = w / 2.0, h / 2.0
+    xA, yA = kA[0].astype(F), kA[1].astype(F)
+    P = np.stack([(xA[good] - cx) * depA[good] / fx, (yA[good] - cy) * depA[good] / fy, depA[good]]).astype(F)
+    last = dict(P=P, octave=kA[4][good].astype(np.int32), angle=kA[3][good].view(F).copy(), desc=dA[good].copy())
+    R, t = np.eye(3, dtype=F).ravel(), np.zeros(3, F)
+    # current frame (pair 1): device arrays only
+    view = frontend.frame_view(fe, 2)
+    sv = fe.slot_view(2)
+    kB, dB = fe.get_keypoints(2)
+    urB, _, _, _ = fe.get_stereo(1)
+    n = kB.shape[1]
+    keys = view["keys"].cpu().numpy().view(frontend.CV_KEYPOINT_DTYPE).reshape(-1)[:n]
+    assert np.array_equal(keys["x"], kB[0].astype(F)) and np.array_equal(keys["y"], kB[1].astype(F))          # Frame.cpp:143-148
+    assert np.array_equal(keys["response"], kB[2].astype(F)) and np.array_equal(keys["angle"].view(np.int32), kB[3])
+    assert np.array_equal(keys["octave"], kB[4]) and np.array_equal(keys["size"], kB[5].astype(F)) and (keys["class_id"] == -1).all()
+    cur_dev = dict(x=view["x"][:n], y=view["y"][:n], octave=view["octave"][:n], angle=view["angle"][:n],
+                   uright=frontend.DevicePtr(sv.u_right), occupied=None, desc=frontend.DevicePtr(sv.desc))
+    dl = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in last.items()}
+    dR, dt = torch.from_numpy(R).cuda(), torch.from_numpy(t).cuda()
+    bounds = dict(min_x=0.0, max_x=float(w), min_y=0.0, max_y=float(h))
+    kw = dict(fx=fx, fy=fy, cx=cx, cy=cy, **bounds, mbf=cfg.mbf, th=7.0, scale_factors=fe.scale, level_mode=0)
+    out = frontend.search_by_projection(dl, cur_dev, dR, dt, **kw)
+    torch.cuda.synchronize()
+    cur_host = dict(x=kB[0].astype(F), y=kB[1].astype(F), octave=kB[4].astype(np.int32), angle=kB[3].view(F).copy(), uright=urB,
+                    occupied=np.zeros(n, np.uint8), desc=dB)
+    want = orc.search_by_projection(last, cur_host, R, t, **kw)
+    got = {k: out[k].cpu().numpy() for k in ("best_idx2", "best_dist", "rot_bin", "cur_match", "hist")}
+    got["nmatches"] = int(out["n_matches"].cpu()[0])
+    assert_same(got, want)
+    assert want["nmatches"] > 30          # the shifted scene really is re-found
+    fe.close()
