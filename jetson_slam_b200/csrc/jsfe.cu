@@ -1049,7 +1049,8 @@ int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pi
     const int word_stores = ((uintptr_t)dst % 4 == 0) && (dst_pitch % 4 == 0) && (dst_stride % 4 == 0);
     // images in flight per output tile: enough blocks to fill the GPU, few enough that the decoded maps are reused
     const int tiles = ((dst_w + 255) / 256) * ((dst_h + 3) / 4);
-    const int gz = std::max(1, std::min(n_images, (148 * 8 + tiles - 1) / tiles));
+    const int groups = (n_images + JSFE_REMAP_UNROLL - 1) / JSFE_REMAP_UNROLL;   // a thread handles its images JSFE_REMAP_UNROLL at a time
+    const int gz = std::max(1, std::min(groups, (148 * 8 + tiles - 1) / tiles));
     jsfe::k_remap_bilinear<<<dim3((dst_w + 255) / 256, (dst_h + 3) / 4, gz), 256, 0, (cudaStream_t)stream>>>(
         src, src_h, src_w, (long long)src_pitch, (long long)src_stride, n_images, map_x, map_y, dst_h, dst_w, dst, (long long)dst_pitch,
         (long long)dst_stride, word_stores);
