@@ -446,7 +446,7 @@ def run_ours(args, cfg):
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e3
         lat = {"pairs_in_flight": 1, "median_ms": float(np.median(ts)), "p95_ms": float(np.percentile(ts, 95)),
-               "how": "jsfe_process_host_pairs(1 pair): pinned H2D + 10 kernels + D2H + sync, wall clock, 200 iterations"}
+               "how": "jsfe_process_host_pairs(1 pair): pinned H2D + one CUDA-graph launch (re-pitch, 10 kernels, result copies) + sync, wall clock, 200 iterations"}
 
     # per-kernel durations (CUDA events on the launching stream around every launch)
     fe.profile(True)
