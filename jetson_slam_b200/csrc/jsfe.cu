@@ -333,7 +333,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
                 worst = std::max(worst, std::fabs((double)T->gauss[j * 7 + k] - (double)T->sep_a[j] * (double)T->sep_b[k]));
         if (worst > 1e-8) { delete T; delete h; return fail(JSFE_ERR_INVALID, "separable blur factors off by %g", worst); }
     }
-    {  // compass pre-test of k_fast_blur_cells: every accepted ring mask must contain `mode` adjacent compass bits
+    {  // compass pre-test of k_fast_cells: every accepted ring mask must contain `mode` adjacent compass bits
         auto compass_ok = [](int m, int mode) {
             const int c[4] = {(m >> 0) & 1, (m >> 4) & 1, (m >> 8) & 1, (m >> 12) & 1};
             for (int s0 = 0; s0 < 4; ++s0) {

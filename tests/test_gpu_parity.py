@@ -74,6 +74,56 @@ def test_stages_match_oracle(name, seed):
     assert (st[0] >= 0).sum() > 0
 
 
+@pytest.mark.parametrize("n_min,n_max,th", [(12, 16, 20), (5, 8, 20), (3, 16, 10), (1, 4, 30), (16, 16, 20), (9, 9, 5)])
+def test_other_arc_bands_match_oracle(n_min, n_max, th):
+    """FAST_N_MIN decides which compass pre-test k_fast_cells may use (3 / 2 / 1 / 0 adjacent compass points); every band must
+    stay exact, including the ones whose pre-test falls back to the reference's two early-outs only."""
+    import dataclasses
+    cfg = dataclasses.replace(CONFIGS["C1"], fast_n_min=n_min, fast_n_max=n_max, th_fast_max=th)
+    L, R = synth.stereo_pair(cfg.height, cfg.width, 5)
+    o = orc.Oracle(**cfg.extractor_kwargs())
+    wk, wd = o.extract(L)
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=1)
+    fe.set_images(L[None])
+    fe.extract(0, 1)
+    kps, desc = fe.get_keypoints(0)
+    cx, cy, cs = fe.cells(0)
+    ox, oy, os_ = o.cells()
+    assert np.array_equal(cs, os_), f"cell scores: {np.count_nonzero(cs != os_)} differ"
+    assert np.array_equal(kps, wk) and np.array_equal(desc, wd)
+    if (n_min, n_max) == (16, 16):
+        assert kps.shape[1] == 0          # the LUT never accepts 0xFFFF (orb_gpu.cpp:366-436)
+    fe.close()
+
+
+def _random_geometry(i):
+    rng = np.random.default_rng(1000 + i)
+    h, w = int(rng.integers(70, 420)), int(rng.integers(70, 520))
+    levels = int(rng.integers(1, 9))
+    scale = float(np.float32(rng.choice([1.1, 1.2, 1.3, 1.5, 2.0])))
+    while levels > 1 and min(h, w) / scale ** (levels - 1) < 45:      # every level needs an interior
+        levels -= 1
+    tile = int(rng.integers(6, 90))
+    fixed = int(rng.integers(0, 2))
+    while not fixed and int(np.float32(tile) * np.float32(1.0 / scale ** (levels - 1))) < 1:
+        tile += 4
+    return dict(height=h, width=w, n_levels=levels, scale_factor=scale, tile_h=tile, tile_w=min(tile, 128),
+                fixed_multi_scale_tile_size=fixed, apply_nms_ms=int(rng.integers(0, 2)), nms_ms_mode_gpu=int(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("i", range(16))
+def test_random_geometries_match_oracle(i):
+    """Odd sizes, tile sizes from 6 to 89 px, 1-8 levels, several scale factors, both cross-scale NMS rules: the block geometry
+    of every kernel (TMA boxes, work maps, phase-A thread grid, tile-row index) is derived from these."""
+    import dataclasses
+    g = _random_geometry(i)
+    cfg = dataclasses.replace(CONFIGS["tiny"], name=f"rand{i}", **g)
+    L, R = synth.stereo_pair(cfg.height, cfg.width, 300 + i)
+    ol, orr, (kl, dl, kr, dr), st = _oracle_pair(cfg, L, R)
+    out = frontend.StereoORB(cfg)(L, R)
+    _assert_pair_equal(out, kl, dl, kr, dr, st, tag=str(g))
+
+
 def _golden_cases():
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "ref_*_seed*.npz"))):
