@@ -258,7 +258,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const jsfe::LevelGeom& g = P.lv[i];
         int items = 0;
         if (g.w > 2 * JSFE_B && g.h > 2 * JSFE_B)
-            items = ((g.w - 2 * JSFE_B + 3) / 4) * ((g.h - 2 * JSFE_B + 31) / 32);
+            items = ((g.w - 2 * JSFE_B + 3) / 4) * ((g.h - 2 * JSFE_B + JSFE_BLUR_ROWS - 1) / JSFE_BLUR_ROWS);
         P.blur_item_start[i + 1] = P.blur_item_start[i] + items;
     }
     P.blur_items_total = P.blur_item_start[P.L];
@@ -465,8 +465,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
         (rc = dev_alloc(h, &P.sad_best, M * cap)))
         return bail(rc);
-    P.blur_eps = JSFE_BLUR_EPS;
-    if (const char* e = getenv("JSFE_DEBUG_BLUR_EPS")) P.blur_eps = (float)atof(e);   // experiments only: breaks exactness
+    P.blur_amb_units = JSFE_BLUR_AMB_UNITS;
+    if (const char* e = getenv("JSFE_DEBUG_BLUR_UNITS")) P.blur_amb_units = (unsigned)atoi(e);   // experiments only: < 3 breaks exactness
     if (cfg->apply_nms_ms && P.L > 1) {
         int ts = 64;
         while (ts < 2 * P.cap) ts <<= 1;

@@ -393,8 +393,10 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
 //  stored byte is always the reference's.  No shared memory: input words come through L1 (each 32-bit word
 //  of a row is shared by 3 neighbouring threads), bytes are widened with PRMT + FADD (0x4B000000 trick).
 // =================================================================================================
-#define JSFE_BLUR_EPS 6.0e-4f
+#define JSFE_BLUR_AMB_UNITS 3u   // ambiguity margin of k_blur in units of 2^-12 (see the kernel)
+#ifndef JSFE_BLUR_ROWS
 #define JSFE_BLUR_ROWS 32
+#endif
 
 // separable factors of the 7x7 weights; the same for every handle (sigma is fixed at 10 in the reference), kept in
 // constant memory so the FFMAs read them as c[][] operands instead of holding 14 registers (74 -> ~60: 4 blocks/SM)
@@ -473,14 +475,14 @@ __global__ void __launch_bounds__(256, 3) k_blur(const __grid_constant__ Params 
                         float A = 0.0f;
 #pragma unroll
                         for (int j = 0; j < 7; ++j) A = __fmaf_rn(c_sep_a[j], q[k][(ph + 1 + j) % 7], A);
-                        // trunc(A) and |A - nearest integer| without F2I: t = 2^23 + rint(A)
-                        const float t = __fadd_rn(A, 8388608.0f);
-                        const float n = __fsub_rn(t, 8388608.0f);
-                        const unsigned v = (__float_as_uint(t) - (n > A ? 1u : 0u)) & 0xFFu;
-                        amb |= (fabsf(__fsub_rn(A, n)) < p.blur_eps ? 1u : 0u) << k;
-                        out |= v << (8 * k);
+                        // A in [0, 256): RZ(A + 2048) = 2048 + floor(A * 4096) / 4096, so bits 12..19 of the sum are trunc(A) and
+                        // bits 0..11 the fraction in units of 2^-12.  Within blur_amb_units (3 units = 7.3e-4 > the 5.3e-4 bound on
+                        // |A - E|) of an integer the truncation of the reference's chain E may differ: flag it.
+                        const unsigned tb = __float_as_uint(__fadd_rz(A, 2048.0f));
+                        amb |= (((tb + p.blur_amb_units) & 0xFFFu) < 2u * p.blur_amb_units ? 1u : 0u) << k;
+                        out |= ((tb >> 12) & 0xFFu) << (8 * k);
                     }
-                    // pixels within blur_eps of an integer (about 0.1 % on textured images, all of a flat region) are decided
+                    // pixels that close to an integer (about 0.15 % on textured images, all of a flat region) are decided
                     // by the exact chain in k_blur_fix; here only their 4-bit mask is recorded (dense, no atomics)
                     amap[(size_t)(y - JSFE_B) * lv.amb_pitch + cg] = (uint8_t)amb;
                     uint8_t* o = dst + (size_t)y * lv.pitch + xg;

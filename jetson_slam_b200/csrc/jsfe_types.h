@@ -84,7 +84,7 @@ struct Params {
     int ms_table_size;                                // power of two >= 2*cap
     int *ms_keys, *ms_sums, *ms_cnts;                 // [slot][ms_table_size]
     uint8_t* ms_drop;                                 // [slot][cap]
-    float blur_eps;                                   // JSFE_BLUR_EPS (6e-4); see DESIGN.md 4.2
+    unsigned blur_amb_units;                          // JSFE_BLUR_AMB_UNITS (3 x 2^-12); see DESIGN.md 4.2
     int fix_items_total;                              // k_blur_fix threads (16 mask bytes each) over all levels
     int fix_item_start[JSFE_MAXL + 1];
 };
