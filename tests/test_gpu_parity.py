@@ -217,6 +217,42 @@ def test_batch_slots_are_independent_and_order_invariant():
                 assert np.array_equal(e["depth"][s_, :n].view(np.int32), want["depth"][s_, :n].view(np.int32))
 
 
+def test_single_chunk_graph_replay_tracks_inputs_and_parameters(monkeypatch):
+    """jsfe_process_host_pairs replays a CUDA graph when the call is one chunk: new images, a changed pair count and changed
+    matcher parameters must all take effect (the graph bakes kernel arguments in), and it must equal the stream path."""
+    cfg = CONFIGS["C1"]
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, 60 + s) for s in range(3)]
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=4)
+
+    def run(imgs, mb, mbf, **kw):
+        e = fe.process_host_pairs(np.stack(imgs), mb, mbf, **kw)
+        return {k: np.array(v) for k, v in e.items() if k != "bytes"}
+
+    def same(a, b):
+        assert np.array_equal(a["n"], b["n"])
+        for s_ in range(len(a["n"])):
+            n = a["n"][s_]
+            assert np.array_equal(a["kps"][s_, :, :n], b["kps"][s_, :, :n]) and np.array_equal(a["desc"][s_, :n], b["desc"][s_, :n])
+            if s_ % 2 == 0:
+                assert np.array_equal(a["u_right"][s_, :n].view(np.int32), b["u_right"][s_, :n].view(np.int32))
+                assert np.array_equal(a["depth"][s_, :n].view(np.int32), b["depth"][s_, :n].view(np.int32))
+
+    g = [run(pairs[i], cfg.mb, cfg.mbf) for i in (0, 1, 0)]                 # capture, replay with other images, replay
+    g2 = run(list(pairs[1]) + list(pairs[2]), cfg.mb, cfg.mbf)               # 2 pairs, still one chunk: re-capture
+    g3 = run(pairs[2], cfg.mb * 0.5, cfg.mbf * 2.0)                          # other matcher parameters: re-capture
+    monkeypatch.setenv("JSFE_NO_GRAPH", "1")
+    s = [run(pairs[i], cfg.mb, cfg.mbf) for i in (0, 1)]
+    s2 = run(list(pairs[1]) + list(pairs[2]), cfg.mb, cfg.mbf)
+    s3 = run(pairs[2], cfg.mb * 0.5, cfg.mbf * 2.0)
+    same(g[0], s[0]); same(g[1], s[1]); same(g[2], s[0]); same(g2, s2); same(g3, s3)
+    assert not np.array_equal(g[0]["kps"], g[1]["kps"])
+    # and against the oracle
+    ol, orr, (kl, dl, kr, dr), st = _oracle_pair(cfg, *pairs[1])
+    n = g[1]["n"][0]
+    assert np.array_equal(g[1]["kps"][0, :, :n], kl) and np.array_equal(g[1]["u_right"][0, :n].view(np.int32), st[0].view(np.int32))
+    fe.close()
+
+
 def test_mask_matches_oracle():
     cfg = CONFIGS["tiny"]
     img, _ = synth.stereo_pair(cfg.height, cfg.width, 5)
