@@ -119,3 +119,24 @@ def test_cuda_rectify_into_slots_then_extract():
         wk, wd = o.extract(want_rect[i])
         assert np.array_equal(kps, wk) and np.array_equal(desc, wd), i
     fe.close()
+
+
+def test_oracle_remap_property_against_cv2():
+    """Hypothesis sweep over small shapes and map values (in range, on the border, far outside, exact grid points)."""
+    cv2 = pytest.importorskip("cv2")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 23), st.integers(1, 29), st.integers(1, 17), st.integers(1, 19), st.integers(0, 2 ** 31 - 1))
+    def check(hs, ws, hd, wd, seed):
+        rng = np.random.default_rng(seed)
+        src = rng.integers(0, 256, size=(hs, ws), dtype=np.uint8)
+        mx = rng.uniform(-3, ws + 3, size=(hd, wd)).astype(np.float32)
+        my = rng.uniform(-3, hs + 3, size=(hd, wd)).astype(np.float32)
+        snap = rng.random((hd, wd)) < 0.3
+        mx[snap] = np.round(mx[snap] * 2) / 2
+        my[snap] = np.round(my[snap])
+        assert np.array_equal(orc.remap_bilinear(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+
+    check()

@@ -1,3 +1,6 @@
+# usage (on the GPU box): VARIANTS="name ..." NCU_KERNELS="k_x ..." NCU_TAG=vN bash tools/gpu_variants.sh
+# runs the GPU tests, the default-size bench with the in-tree libjsfe.so and with every variants/libjsfe_<name>.so, then optional
+# `ncu --set full` captures of the named kernels into gpurun_out/prof_<tag>_<kernel>.ncu-rep (read here with tools/ncu_summary.py)
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 cp jetson_slam_b200/libjsfe.so /tmp/base.so
 python bench.py --steps 10 --warmup 3 --no-ref-cuda > gpurun_out/b_base.json 2> gpurun_out/b_base.err; echo base; python tools/bench_brief.py gpurun_out/b_base.json
