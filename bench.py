@@ -263,6 +263,28 @@ def remap_microbench(n_images=64, iters=50):
             "alg_bytes_per_launch": alg, "gbs": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
 
 
+def opencv_orb_pairs_per_s(cfg, pair, iters=5):
+    """Colour only, NOT parity-comparable (a different algorithm: the reference contains no OpenCV extractor): OpenCV's CPU ORB
+    (cv2.ORB_create(2000, 1.2, 8)) on both eyes + brute-force Hamming matching, one thread."""
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        orb = cv2.ORB_create(nfeatures=2000, scaleFactor=1.2, nlevels=cfg.n_levels)
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        L, R = pair
+        orb.detectAndCompute(L, None)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            kl, dl = orb.detectAndCompute(L, None)
+            kr, dr = orb.detectAndCompute(R, None)
+            if dl is not None and dr is not None:
+                bf.match(dl, dr)
+        dt = (time.perf_counter() - t0) / iters
+        return {"value": 1.0 / dt, "unit": UNIT, "cores": 1, "keypoints": len(kl), "note": "OpenCV %s CPU ORB + BFMatcher; different algorithm, not parity-comparable" % cv2.__version__}
+    except Exception as e:
+        return {"unavailable": repr(e)[:120]}
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -548,6 +570,7 @@ def run_ours(args, cfg):
         if ref_cuda is not None:
             line["ref_cuda"] = ref_cuda
         if world == 1:
+            line["opencv_cpu_orb"] = opencv_orb_pairs_per_s(cfg, pairs[0])
             try:
                 line["adjacent"] = {"search_by_projection": sbp_microbench(), "remap_bilinear": remap_microbench()}
             except Exception as e:   # adjacent-row colour must never break the headline line

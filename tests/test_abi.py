@@ -55,3 +55,18 @@ def test_bad_arguments_are_rejected_before_touching_cuda():
     assert lib.jsfe_create(None, None) == -1
     assert b"null" in lib.jsfe_last_error()
     assert lib.jsfe_max_keypoints(None) == -1
+
+
+def test_header_is_plain_c99_and_layouts_match_the_bindings(tmp_path):
+    """include/jsfe.h must be consumable by a C compiler (cgo / JNI / ctypes generators read it), and the ctypes images of its
+    structs must have the C sizes."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "jsfe.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(jsfe_config), '
+                   'sizeof(jsfe_slot_view), sizeof(jsfe_host_results), sizeof(jsfe_sbp_args), sizeof(jsfe_cv_keypoint)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(frontend._Config), C.sizeof(frontend.SlotView), C.sizeof(frontend.HostResults), C.sizeof(frontend._SbpArgs),
+                     frontend.CV_KEYPOINT_DTYPE.itemsize]
