@@ -171,6 +171,13 @@ int jsfe_download_results(jsfe_handle* h, int first_slot, int n, jsfe_host_resul
  * compute.  Synchronous: on return `out` points at the handle's pinned result slabs for slots [0, 2*n_pairs). */
 int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
                             float mb, float mbf, jsfe_host_results* out);
+/* The same call split at its synchronisation point: _begin enqueues the whole batch and returns, _end waits and hands out the
+ * result slabs.  One batch per handle may be in flight; with two handles a single host thread keeps two batches in flight
+ * (begin(h1), end(h0), begin(h0), end(h1), ...), so the upload of one batch overlaps the kernels of the other and sustained
+ * host-to-host throughput approaches the device-resident rate.  `images` must stay valid (pinned recommended) until _end. */
+int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
+                                  float mb, float mbf);
+int jsfe_process_host_pairs_end(jsfe_handle* h, jsfe_host_results* out);
 
 /* ---- adjacent rows: stateless helpers of the tracking thread.  All pointers are DEVICE pointers,
  * work is enqueued on `stream` and NOT synchronised (the compat shims synchronise, as the reference does).

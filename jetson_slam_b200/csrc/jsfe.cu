@@ -105,6 +105,8 @@ struct jsfe_handle {
     int pg_pairs = 0, pg_th_high = 0, pg_th_low = 0;
     float pg_mb = 0.f, pg_mbf = 0.f;
     bool pg_disabled = false;
+    bool repitch_kernel = true;   // JSFE_NO_REPITCH_KERNEL=1: device-to-device 2-D copies instead (copy engine)
+    int pending_pairs = 0;   // batch enqueued by jsfe_process_host_pairs_begin and not yet collected
 };
 
 namespace {
@@ -503,6 +505,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         if (const char* e = getenv("JSFE_CHUNK_IMAGES")) h->chunk_images = atoi(e);
     }
     if (const char* e = getenv("JSFE_NO_OVERLAP")) h->overlap_blur = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("JSFE_NO_REPITCH_KERNEL")) h->repitch_kernel = atoi(e) == 0;
     if (cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
@@ -559,6 +562,15 @@ int jsfe_set_images(jsfe_handle* h, int first_slot, int n, const uint8_t* src, i
     if (!src || row_pitch < h->P.W0) return fail(JSFE_ERR_INVALID, "bad source image pointer / pitch");
     CU(cudaSetDevice(h->device));
     const jsfe::LevelGeom& g = h->P.lv[0];
+    if (src_is_device && row_pitch == g.w && h->repitch_kernel) {
+        // contiguous rows on the device (the staging buffer of jsfe_process_host_pairs, or any packed device frame)
+        const int chunks = g.h * (g.pitch / 16);
+        jsfe::k_repitch<<<dim3((chunks + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(
+            src, (long long)row_pitch, (long long)image_stride, src, src + (size_t)(n - 1) * image_stride + (size_t)g.h * row_pitch,
+            g.img + (size_t)first_slot * g.slot_stride, g.pitch, g.slot_stride, g.h, g.w);
+        CU(cudaGetLastError());
+        return JSFE_OK;
+    }
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (image_stride == row_pitch * (int64_t)g.h && g.slot_stride == (size_t)g.pitch * g.h) {
         // rows of consecutive images are equally spaced on both sides: one 2-D copy for the whole batch
@@ -840,11 +852,12 @@ int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, 
     return JSFE_OK;
 }
 
-int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
-                            float mb, float mbf, jsfe_host_results* out) {
+int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
+                                  float mb, float mbf) {
     int rc = check_slots(h, 0, 2 * n_pairs);
     if (rc) return rc;
-    if (!images || !out || n_pairs < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (!images || n_pairs < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (h->pending_pairs) return fail(JSFE_ERR_INVALID, "a batch is already in flight on this handle (call jsfe_process_host_pairs_end)");
     CU(cudaSetDevice(h->device));
     const jsfe::Params& P = h->P;
     const jsfe::LevelGeom& g = P.lv[0];
@@ -938,19 +951,39 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
         if ((rc = enqueue_results(s0, ns, h->st_d2h))) break;
     }
     h->profiling = saved_prof;
+    if (rc) {   // something failed while enqueueing: drain what was enqueued and report
+        cudaStreamSynchronize(h->st_h2d); cudaStreamSynchronize(h->st_comp); cudaStreamSynchronize(h->st_d2h);
+        return rc;
+    }
+    h->pending_pairs = n_pairs;
+    return JSFE_OK;
+}
+
+int jsfe_process_host_pairs_end(jsfe_handle* h, jsfe_host_results* out) {
+    if (!h || !out) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (!h->pending_pairs) return fail(JSFE_ERR_INVALID, "no batch in flight on this handle");
+    CU(cudaSetDevice(h->device));
+    const int n_pairs = h->pending_pairs;
+    h->pending_pairs = 0;
     cudaError_t e1 = cudaStreamSynchronize(h->st_h2d), e2 = cudaStreamSynchronize(h->st_comp), e3 = cudaStreamSynchronize(h->st_d2h);
-    if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return fail(JSFE_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
-    const size_t N = (size_t)2 * n_pairs;
+    const size_t N = (size_t)2 * n_pairs, cap = (size_t)h->P.cap;
     out->n_keypoints = h->h_n;
     out->kps = h->h_kps;
     out->desc = h->h_desc;
     out->u_right = h->h_ur;
     out->depth = h->h_dp;
-    out->capacity = P.cap;
+    out->capacity = h->P.cap;
     out->bytes = (int64_t)(N * 4 + N * 6 * cap * 4 + N * cap * 32 + 2 * N * cap * 4);
     return JSFE_OK;
+}
+
+int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
+                            float mb, float mbf, jsfe_host_results* out) {
+    if (!out) return fail(JSFE_ERR_INVALID, "bad argument");
+    const int rc = jsfe_process_host_pairs_begin(h, n_pairs, images, chunk_pairs, th_high, th_low, mb, mbf);
+    return rc ? rc : jsfe_process_host_pairs_end(h, out);
 }
 
 int jsfe_project_points(int n, const float* px, const float* py, const float* pz, const float* rcw9, const float* tcw3, float fx,

@@ -48,6 +48,44 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // =================================================================================================
 __device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(v | 0x4B000000u) - 8388608.0f; }
 
+// K0  k_repitch: device-side copy of n images with contiguous rows (row pitch = w, as a host buffer has them) into the
+//     16-byte-pitched level-0 slots; pad bytes [w, pitch) are written as 0.  A kernel rather than cudaMemcpy2DAsync so that
+//     it never queues behind another batch's long host-to-device copy on a copy engine (two batches in flight).
+//     Thread = one 16-byte chunk of a destination row; the source is read as aligned 32-bit words and funnel-shifted.
+__global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ src, long long src_row_pitch, long long src_image_stride,
+                                                 const uint8_t* __restrict__ src_begin, const uint8_t* __restrict__ src_end, uint8_t* __restrict__ dst, int pitch,
+                                                 unsigned long long slot_stride, int h, int w) {
+    const int cpr = pitch >> 4;                                   // chunks per row
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= h * cpr) return;
+    const int row = id / cpr, c = id - row * cpr, x = c << 4;
+    const uint8_t* s = src + (size_t)blockIdx.y * src_image_stride + (size_t)row * src_row_pitch + x;
+    const int nb = min(16, w - x);                                // valid bytes of this chunk (<= 0: pure padding)
+    uint32_t o[4] = {0u, 0u, 0u, 0u};
+    if (nb > 0) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        if (reinterpret_cast<const uint8_t*>(q) >= src_begin && reinterpret_cast<const uint8_t*>(q + 5) <= src_end) {
+            const unsigned sh = (unsigned)(a & 3u) * 8u;
+            uint32_t wv[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) wv[k] = __ldg(q + k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+        } else {                                                  // first / last words of the buffer: stay inside it
+            for (int b = 0; b < nb; ++b) o[b >> 2] |= (uint32_t)__ldg(s + b) << (8 * (b & 3));
+        }
+        if (nb < 16) {                                            // zero the bytes beyond the image width
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int keep = nb - 4 * k;                      // bytes of word k that belong to the row
+                o[k] = keep >= 4 ? o[k] : keep <= 0 ? 0u : (o[k] & ((1u << (8 * keep)) - 1u));
+            }
+        }
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)blockIdx.y * slot_stride + (size_t)row * pitch + x) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 #define JSFE_PYR_ROWS 32   // rows per block tile (8 y-lanes x 4 rows each)
 
 __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params p, int slot0) {

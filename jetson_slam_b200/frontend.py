@@ -84,6 +84,8 @@ def lib():
         L.jsfe_project_points.argtypes = [C.c_int] + [vp] * 5 + [f] * 8 + [vp] * 4 + [vp]
         L.jsfe_hamming_pairs.argtypes = [C.c_int] + [vp] * 5 + [vp]
         L.jsfe_in_frustum.argtypes = [C.c_int] + [vp] * 12 + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
+        L.jsfe_process_host_pairs_begin.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, f, f]
+        L.jsfe_process_host_pairs_end.argtypes = [vp, C.POINTER(HostResults)]
         L.jsfe_build_frame_grid.argtypes = [C.c_int, vp, vp, f, f, f, f, vp, vp, vp]
         L.jsfe_search_by_projection.argtypes = [vp, vp]
         L.jsfe_frame_view.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
@@ -215,19 +217,41 @@ class Frontend:
             "u_right": as_np(r.u_right, (n, cap)), "depth": as_np(r.depth, (n, cap)), "bytes": r.bytes,
         }
 
-    def process_host_pairs(self, images, mb, mbf, chunk_pairs=0, th_high=100, th_low=50):
-        """End-to-end: images u8 [2*n_pairs, H, W] in host memory (L0,R0,L1,R1,...) -> dict of pinned result views.
-        Upload, extract, match and download are pipelined in chunks over three CUDA streams; synchronous."""
-        a = np.asarray(images)
-        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[1:] != (self.height, self.width) or not a.flags.c_contiguous or a.shape[0] % 2:
-            raise ValueError("images must be C-contiguous uint8 [2*n_pairs, H, W]")
-        n = a.shape[0]
-        r = HostResults()
-        _check(lib().jsfe_process_host_pairs(self._h, n // 2, a.ctypes.data, chunk_pairs, th_high, th_low, mb, mbf, C.byref(r)))
+    def _host_results(self, r, n):
         cap = r.capacity
         as_np = np.ctypeslib.as_array
         return {"n": as_np(r.n_keypoints, (n,)), "kps": as_np(r.kps, (n, 6, cap)), "desc": as_np(r.desc, (n, cap, 32)),
                 "u_right": as_np(r.u_right, (n, cap)), "depth": as_np(r.depth, (n, cap)), "bytes": r.bytes}
+
+    @staticmethod
+    def _check_images(a, height, width):
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[1:] != (height, width) or not a.flags.c_contiguous or a.shape[0] % 2:
+            raise ValueError("images must be C-contiguous uint8 [2*n_pairs, H, W]")
+
+    def process_host_pairs(self, images, mb, mbf, chunk_pairs=0, th_high=100, th_low=50):
+        """End-to-end: images u8 [2*n_pairs, H, W] in host memory (L0,R0,L1,R1,...) -> dict of pinned result views.
+        Upload, extract, match and download are pipelined in chunks over three CUDA streams; synchronous."""
+        a = np.asarray(images)
+        self._check_images(a, self.height, self.width)
+        n = a.shape[0]
+        r = HostResults()
+        _check(lib().jsfe_process_host_pairs(self._h, n // 2, a.ctypes.data, chunk_pairs, th_high, th_low, mb, mbf, C.byref(r)))
+        return self._host_results(r, n)
+
+    def process_host_pairs_begin(self, images, mb, mbf, chunk_pairs=0, th_high=100, th_low=50):
+        """Enqueue a batch and return (jsfe_process_host_pairs_begin); `images` must stay alive until process_host_pairs_end."""
+        a = np.asarray(images)
+        self._check_images(a, self.height, self.width)
+        self._inflight = a
+        _check(lib().jsfe_process_host_pairs_begin(self._h, a.shape[0] // 2, a.ctypes.data, chunk_pairs, th_high, th_low, mb, mbf))
+
+    def process_host_pairs_end(self):
+        """Wait for the batch enqueued by process_host_pairs_begin -> dict of pinned result views."""
+        r = HostResults()
+        _check(lib().jsfe_process_host_pairs_end(self._h, C.byref(r)))
+        n = self._inflight.shape[0]
+        self._inflight = None
+        return self._host_results(r, n)
 
     def slot_view(self, slot):
         v = SlotView()

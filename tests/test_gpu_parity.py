@@ -253,6 +253,38 @@ def test_single_chunk_graph_replay_tracks_inputs_and_parameters(monkeypatch):
     fe.close()
 
 
+def test_begin_end_two_handles_in_flight_equal_the_blocking_call():
+    cfg = CONFIGS["C1"]
+    batches = [np.stack([im for s_ in range(3) for im in synth.stereo_pair(cfg.height, cfg.width, 80 + 3 * b + s_)]) for b in range(3)]
+    fes = [frontend.Frontend(**cfg.extractor_kwargs(), max_images=6) for _ in range(2)]
+    want = []
+    for b in batches:
+        e = fes[0].process_host_pairs(b, cfg.mb, cfg.mbf)
+        want.append({k: np.array(v) for k, v in e.items() if k != "bytes"})
+    got = []
+    fes[0].process_host_pairs_begin(batches[0], cfg.mb, cfg.mbf, chunk_pairs=3)
+    with pytest.raises(frontend.JsfeError):
+        fes[0].process_host_pairs_begin(batches[1], cfg.mb, cfg.mbf)          # one batch per handle
+    for k in (1, 2):
+        fes[k % 2].process_host_pairs_begin(batches[k], cfg.mb, cfg.mbf, chunk_pairs=2 if k == 1 else 3)
+        e = fes[(k - 1) % 2].process_host_pairs_end()
+        got.append({kk: np.array(v) for kk, v in e.items() if kk != "bytes"})
+    e = fes[0].process_host_pairs_end()
+    got.append({kk: np.array(v) for kk, v in e.items() if kk != "bytes"})
+    with pytest.raises(frontend.JsfeError):
+        fes[0].process_host_pairs_end()                                          # nothing in flight
+    for g, w in zip(got, want):
+        assert np.array_equal(g["n"], w["n"])
+        for s_ in range(6):
+            n = w["n"][s_]
+            assert np.array_equal(g["kps"][s_, :, :n], w["kps"][s_, :, :n]) and np.array_equal(g["desc"][s_, :n], w["desc"][s_, :n])
+            if s_ % 2 == 0:
+                assert np.array_equal(g["u_right"][s_, :n].view(np.int32), w["u_right"][s_, :n].view(np.int32))
+                assert np.array_equal(g["depth"][s_, :n].view(np.int32), w["depth"][s_, :n].view(np.int32))
+    for f in fes:
+        f.close()
+
+
 def test_mask_matches_oracle():
     cfg = CONFIGS["tiny"]
     img, _ = synth.stereo_pair(cfg.height, cfg.width, 5)
