@@ -49,3 +49,38 @@ def test_frame_hotpath_through_cpp_shims_matches_oracle(name, tmp_path):
     assert np.array_equal(kl, okl) and np.array_equal(kr, okr)
     assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
     assert np.array_equal(ur.view(np.int32), our.view(np.int32)) and np.array_equal(dp.view(np.int32), odp.view(np.int32))
+
+
+C_BIN = os.path.join(ROOT, "tests", "c", "pair_from_c")
+
+
+def test_plain_c_consumer_builds():
+    import __graft_entry__ as g
+    g.build()
+    assert os.path.exists(C_BIN)
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_matches_the_python_binding(tmp_path):
+    """The same pair through a C99 program that includes only include/jsfe.h and through the ctypes binding."""
+    from jetson_slam_b200 import frontend, synth
+    from jetson_slam_b200.configs import CONFIGS
+    import __graft_entry__ as g
+    g.build()
+    cfg = CONFIGS["C1"]
+    L, R = synth.stereo_pair(cfg.height, cfg.width, 11)
+    raw = tmp_path / "pair.raw"
+    raw.write_bytes(L.tobytes() + R.tobytes())
+    out = subprocess.run([C_BIN, str(cfg.height), str(cfg.width), str(cfg.n_levels), str(cfg.tile_h), str(raw), repr(cfg.mb), repr(cfg.mbf)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    nl, nr, nd, chk = (int(v) for v in out.stdout.split())
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=2)
+    r = fe.process_host_pairs(np.stack([L, R]), cfg.mb, cfg.mbf)
+    assert (nl, nr) == (int(r["n"][0]), int(r["n"][1])) and nd == int((r["depth"][0, :nl] > 0).sum())
+    s = 0
+    for i in range(nl):
+        for pl in range(6):
+            s = (s * 1000003 + (int(r["kps"][0, pl, i]) & 0xFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+    assert s == chk
+    fe.close()
