@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //          and Tile_unrolling_reduction_kernel_v2              (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397)
 //
 //  FAST is integer-ALU-bound, not HBM-bound, so the work is cut before it is spread:
-//   phase A  4 pixels per thread, packed-byte SWAR: |p-v| with VABSDIFF4, per-byte compares in the byte
+//   phase A  8 pixels per thread and iteration, packed-byte SWAR: |p-v| with VABSDIFF4, per-byte compares in the byte
 //            MSBs.  Only the 4 compass ring points are read; a pixel survives iff the reference's two
 //            early-outs do not fire AND enough adjacent compass points are all brighter / all darker for ANY
 //            accepted arc to exist (a necessary condition derived from FAST_N_MIN and verified against the
 //            LUT at create time).  Survivors go to a shared-memory work list (ballot-compacted).
 //   phase B  the work list is evaluated densely, 4 ring points per packed word: masks, LUT, SAD (VABSDIFF4.ACC).
-//   phase C  the work list is walked once more: positive scores do the 3x3 NMS test and one shared-memory
+//   phase C  the positives list (filled by phase B) is walked: each positive score does the 3x3 NMS test and one shared-memory
 //            atomicMax per cell on a key that encodes the reference's tie-break order:
 //            (score desc, column priority of the reference's smem tree asc, y-lane (y-y0)%T asc, y asc).
 //  Every pixel rejected in phase A has score 0 in the reference too, so scores are bit-identical.
