@@ -870,7 +870,7 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
     }
     if (chunk_pairs < 1) chunk_pairs = 32;
     // chunk schedule: a short first chunk (C/4, then C/2) so that compute starts early, full chunks after, and a short
-    // last chunk (C/2, C/4) so that little D2H is left when compute ends; the call is blocking, only its inside pipelines
+    // last chunk (C/2, C/4) so that little D2H is left when compute ends
     std::vector<int> sizes;
     {
         int left = n_pairs;
@@ -892,8 +892,12 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
         h->ev_done.push_back(b);
     }
     const size_t cap = P.cap;
-    const bool saved_prof = h->profiling;
-    h->profiling = false;
+    struct ProfilingOff {   // per-kernel event spans are not recorded inside the pipeline; restored on every exit path
+        jsfe_handle* h;
+        bool saved;
+        explicit ProfilingOff(jsfe_handle* hh) : h(hh), saved(hh->profiling) { hh->profiling = false; }
+        ~ProfilingOff() { h->profiling = saved; }
+    } profiling_off(h);
     auto enqueue_results = [&](int s0, int ns, cudaStream_t st) -> int {
         CU(cudaMemcpyAsync(h->h_n + s0, P.n_kp + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->h_kps + (size_t)s0 * 6 * cap, P.kps + (size_t)s0 * 6 * cap, (size_t)ns * 6 * cap * 4, cudaMemcpyDeviceToHost, st));
@@ -950,7 +954,6 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
         CU(cudaStreamWaitEvent(h->st_d2h, h->ev_done[c], 0));
         if ((rc = enqueue_results(s0, ns, h->st_d2h))) break;
     }
-    h->profiling = saved_prof;
     if (rc) {   // something failed while enqueueing: drain what was enqueued and report
         cudaStreamSynchronize(h->st_h2d); cudaStreamSynchronize(h->st_comp); cudaStreamSynchronize(h->st_d2h);
         return rc;
