@@ -293,3 +293,16 @@ def test_device_resident_chain_extract_stereo_view_grid_search():
     assert_same(got, want)
     assert want["nmatches"] > 30          # the shifted scene really is re-found
     fe.close()
+
+
+def test_oracle_regression_pins():
+    """The oracle restatement must not drift: fixed seeded scenes against tests/golden/adj_sbp_oracle.npz (tools/make_golden_adjacent.py)."""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "adj_sbp_oracle.npz"))
+    for mode in (0, 1, 2):
+        last, cur, R, t = make_scene(n_cur=900, n_last=700, seed=40 + mode)
+        r = run_oracle(last, cur, R, t, 7.0 if mode != 1 else 15.0, mode)
+        assert r["nmatches"] == int(g[f"m{mode}_nmatches"]) and r["nmatches"] > 100
+        for k in ("best_idx2", "best_dist", "rot_bin", "cur_match", "hist"):
+            assert np.array_equal(np.asarray(r[k]), g[f"m{mode}_{k}"]), (mode, k)
