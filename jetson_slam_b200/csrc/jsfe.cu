@@ -77,6 +77,7 @@ struct jsfe_handle {
     int max_images = 0;
     jsfe::Params P;       // host copy of the kernel parameter block
     size_t fast_smem = 0; // dynamic shared memory of k_fast_cells
+    void (*fast_kernel)(jsfe::Params, jsfe::TmaMaps, int) = nullptr;   // the k_fast_cells<compass mode, mask> instance of this handle
     std::vector<void*> dev_allocs;
     // pinned staging for jsfe_download_results / jsfe_get_*
     int32_t* h_n = nullptr;
@@ -107,6 +108,7 @@ struct jsfe_handle {
     bool pg_disabled = false;
     bool repitch_kernel = true;   // JSFE_NO_REPITCH_KERNEL=1: device-to-device 2-D copies instead (copy engine)
     int pending_pairs = 0;   // batch enqueued by jsfe_process_host_pairs_begin and not yet collected
+    bool pipe_ready = false; // d_stage and the three pipeline streams exist
 };
 
 namespace {
@@ -238,7 +240,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         g.block_offset = items;
         items += g.blocks_per_row * g.n_tile_h;
         const size_t gw = (size_t)g.cells_per_block * g.tile_w;
-        const size_t pw = align_up(gw + 8 + 15, 16), pr = g.tile_h + 8;   // covers X0+GW+4-gx0 with gx0 = floor16(X0-4)
+        const size_t pw = JSFE_FAST_PW, pr = g.tile_h + 8;   // fixed pitch: covers X0+GW+4-gx0 (<= 19 + 192 + 4) with gx0 = floor16(X0-4)
+        if (gw + 8 + 15 > pw) { delete h; return fail(JSFE_ERR_INVALID, "internal: cell group wider than the staged tile"); }
         g.tile_pw = (int)pw;
         // phase A thread grid: 8-pixel column groups covering score columns [cs0-0, cs0+gw+1], cs0 = X0-1-floor16(X0-4) in [3,18]
         int ngx = 1;
@@ -249,7 +252,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         for (unsigned t = 0; t < 256; ++t)
             if (((t * g.fast_ngx_inv) >> 16) != t / (unsigned)ngx) { delete h; return fail(JSFE_ERR_INVALID, "internal: phase A reciprocal is not exact"); }
         const size_t sw = (gw + 2 + 7) & ~(size_t)7;
-        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 9 / 4 + 64);  // pixels + scores + work list + positives (1/4)
+        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 2 + 64);  // pixels + scores + work list (the positives live in its gap)
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
         if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 31) / 32);
         if (g.w >= 16384 || g.h >= 16384) { delete h; return fail(JSFE_ERR_INVALID, "images larger than 16383 pixels are not supported"); }
@@ -353,6 +356,17 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             if (ok) break;
         }
         P.compass_mode = mode;
+    }
+    P.fast_q_thresh = P.threshold >= 3 ? (P.threshold - 3) / 4 + 1 : 0;
+    if (P.threshold < 0 || P.threshold > 255) { delete T; delete h; return fail(JSFE_ERR_INVALID, "th_fast_max must be in [0,255]"); }
+    P.fast_list_cap = 0;
+    if (const char* e = getenv("JSFE_DEBUG_FAST_CAP")) P.fast_list_cap = std::max(0, atoi(e));   // tests: force the overflow paths
+    for (int m = 0; m < 0x10000; ++m) {   // LUT in the bit order k_fast_cells' flag merge produces (see fast_eval)
+        if (!((T->lut_bits[m >> 5] >> (m & 31)) & 1u)) continue;
+        unsigned idx = 0;
+        for (int k = 0; k < 16; ++k)
+            if (m & (1 << k)) idx |= 1u << (4 * (k & 3) + 3 - (k >> 2));   // ring k = byte k%4 of word k/4
+        T->lut_perm[idx >> 5] |= 1u << (idx & 31);
     }
     for (int i = 0; i < 512; ++i) {  // orb_bitpattern.cpp:266-273
         T->pat_x[i] = (int8_t)kPattern[2 * i];
@@ -488,8 +502,15 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         cudaMallocHost((void**)&h->h_dp, M * cap * sizeof(float) + 16) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_misc, 5 * cap * sizeof(int32_t) + 16) != cudaSuccess)
         return bail(fail(JSFE_ERR_CUDA, "pinned host allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    {
+        using jsfe::k_fast_cells;
+        void (*const table[4][2])(jsfe::Params, jsfe::TmaMaps, int) = {
+            {k_fast_cells<0, false>, k_fast_cells<0, true>}, {k_fast_cells<1, false>, k_fast_cells<1, true>},
+            {k_fast_cells<2, false>, k_fast_cells<2, true>}, {k_fast_cells<3, false>, k_fast_cells<3, true>}};
+        h->fast_kernel = table[P.compass_mode][cfg->mask ? 1 : 0];
+    }
     if (h->fast_smem + 4096 > 48 * 1024) {  // dynamic + static shared memory beyond 48 KB needs the opt-in
-        if (cudaFuncSetAttribute(jsfe::k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(h->fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem) != cudaSuccess)
             return bail(fail(JSFE_ERR_CUDA, "k_fast_cells needs %zu bytes of shared memory", h->fast_smem));
     }
     {   // sub-batch size: images whose level-0 + levels + blurred levels fit in ~60% of L2
@@ -625,7 +646,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     }
     {
         StageTimer t(h, st, 1);
-        jsfe::k_fast_cells<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, h->tma, first_slot);
+        h->fast_kernel<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, h->tma, first_slot);
     }
     if ((rc = post_launch(h, "k_fast_cells"))) return rc;
     if (P.blur_items_total > 0) {
@@ -862,11 +883,19 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
     const jsfe::Params& P = h->P;
     const jsfe::LevelGeom& g = P.lv[0];
     const size_t img_bytes = (size_t)g.h * g.w;
-    if (!h->d_stage) {  // first use: staging buffer in the host layout (contiguous rows), streams, events
-        CU(cudaMalloc((void**)&h->d_stage, img_bytes * h->max_images));
-        CU(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    if (!h->pipe_ready) {  // first use: staging buffer in the host layout (contiguous rows) and the three streams; all or nothing
+        cudaError_t e = cudaMalloc((void**)&h->d_stage, img_bytes * h->max_images);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            if (h->d_stage) { cudaFree(h->d_stage); h->d_stage = nullptr; }
+            if (h->st_h2d) { cudaStreamDestroy(h->st_h2d); h->st_h2d = nullptr; }
+            if (h->st_comp) { cudaStreamDestroy(h->st_comp); h->st_comp = nullptr; }
+            if (h->st_d2h) { cudaStreamDestroy(h->st_d2h); h->st_d2h = nullptr; }
+            return fail(JSFE_ERR_CUDA, "pipeline set-up failed: %s", cudaGetErrorString(e));
+        }
+        h->pipe_ready = true;
     }
     if (chunk_pairs < 1) chunk_pairs = 32;
     // chunk schedule: a short first chunk (C/4, then C/2) so that compute starts early, full chunks after, and a short
@@ -875,13 +904,17 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
     {
         int left = n_pairs;
         const int ramp[2] = {std::max(1, chunk_pairs / 4), std::max(1, chunk_pairs / 2)};
-        const bool ramped = n_pairs >= 3 * chunk_pairs && !getenv("JSFE_NO_RAMP");
+        // the ramp needs room for its head and its tail plus at least one pair in between
+        const bool ramped = n_pairs >= 3 * chunk_pairs && n_pairs > 2 * (ramp[0] + ramp[1]) && !getenv("JSFE_NO_RAMP");
         if (ramped)
             for (int r = 0; r < 2; ++r) { sizes.push_back(ramp[r]); left -= ramp[r]; }
         const int tail = ramped ? ramp[0] + ramp[1] : 0;
         while (left - tail > 0) { const int c = std::min(chunk_pairs, left - tail); sizes.push_back(c); left -= c; }
         if (ramped)
             for (int r = 1; r >= 0; --r) { sizes.push_back(ramp[r]); left -= ramp[r]; }
+        int total = 0;
+        for (int c : sizes) total += c;
+        if (left != 0 || total != n_pairs) return fail(JSFE_ERR_INVALID, "internal: chunk schedule covers %d of %d pairs", total, n_pairs);
     }
     const int n_chunks = (int)sizes.size();
     while ((int)h->ev_up.size() < n_chunks) {
@@ -933,25 +966,36 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
             }
         }
         if (h->pair_graph) {
-            CU(cudaMemcpyAsync(h->d_stage, images, img_bytes * 2 * n_pairs, cudaMemcpyHostToDevice, h->st_comp));
-            CU(cudaGraphLaunch(h->pair_graph, h->st_comp));
+            cudaError_t e = cudaMemcpyAsync(h->d_stage, images, img_bytes * 2 * n_pairs, cudaMemcpyHostToDevice, h->st_comp);
+            if (e == cudaSuccess) e = cudaGraphLaunch(h->pair_graph, h->st_comp);
+            if (e != cudaSuccess) {   // drain whatever was enqueued, then report
+                cudaStreamSynchronize(h->st_comp);
+                return fail(JSFE_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
+            }
             done_by_graph = true;
         }
     }
+    // from here on nothing returns before the drain below: a failed enqueue must not leave work in flight with pending_pairs == 0
+    auto cu = [&](cudaError_t e, const char* what) -> bool {
+        if (e == cudaSuccess) return true;
+        rc = fail(JSFE_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        return false;
+    };
     for (int c = 0, p0 = 0; c < n_chunks && !done_by_graph; p0 += sizes[c], ++c) {
         const int np = sizes[c];
         const int s0 = 2 * p0, ns = 2 * np;
         // 1. one contiguous H2D per chunk (2-D copies with odd row widths run far below PCIe speed)
-        CU(cudaMemcpyAsync(h->d_stage + img_bytes * s0, images + img_bytes * s0, img_bytes * ns, cudaMemcpyHostToDevice, h->st_h2d));
-        CU(cudaEventRecord(h->ev_up[c], h->st_h2d));
+        if (!cu(cudaMemcpyAsync(h->d_stage + img_bytes * s0, images + img_bytes * s0, img_bytes * ns, cudaMemcpyHostToDevice, h->st_h2d), "upload") ||
+            !cu(cudaEventRecord(h->ev_up[c], h->st_h2d), "cudaEventRecord"))
+            break;
         // 2. re-pitch into the slots (device-to-device), extract, match
-        CU(cudaStreamWaitEvent(h->st_comp, h->ev_up[c], 0));
+        if (!cu(cudaStreamWaitEvent(h->st_comp, h->ev_up[c], 0), "cudaStreamWaitEvent")) break;
         if ((rc = jsfe_set_images(h, s0, ns, h->d_stage + img_bytes * s0, g.w, (int64_t)img_bytes, 1, h->st_comp))) break;
         if ((rc = jsfe_extract(h, s0, ns, h->st_comp))) break;
         if ((rc = jsfe_stereo_match(h, p0, np, th_high, th_low, mb, mbf, h->st_comp))) break;
-        CU(cudaEventRecord(h->ev_done[c], h->st_comp));
+        if (!cu(cudaEventRecord(h->ev_done[c], h->st_comp), "cudaEventRecord")) break;
         // 3. results of this chunk back to pinned host memory while the next chunk computes
-        CU(cudaStreamWaitEvent(h->st_d2h, h->ev_done[c], 0));
+        if (!cu(cudaStreamWaitEvent(h->st_d2h, h->ev_done[c], 0), "cudaStreamWaitEvent")) break;
         if ((rc = enqueue_results(s0, ns, h->st_d2h))) break;
     }
     if (rc) {   // something failed while enqueueing: drain what was enqueued and report

@@ -141,17 +141,26 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //          and Tile_unrolling_reduction_kernel_v2              (src/cuda/orb_FAST_apply_NMS_G.cu:1178-1397)
 //
 //  FAST is integer-ALU-bound, not HBM-bound, so the work is cut before it is spread:
-//   phase A  8 pixels per thread and iteration, packed-byte SWAR: |p-v| with VABSDIFF4, per-byte compares in the byte
-//            MSBs.  Only the 4 compass ring points are read; a pixel survives iff the reference's two
-//            early-outs do not fire AND enough adjacent compass points are all brighter / all darker for ANY
-//            accepted arc to exist (a necessary condition derived from FAST_N_MIN and verified against the
-//            LUT at create time).  Survivors go to a shared-memory work list (ballot-compacted).
-//   phase B  the work list is evaluated densely, 4 ring points per packed word: masks, LUT, SAD (VABSDIFF4.ACC).
-//   phase C  the positives list (filled by phase B) is walked: each positive score does the 3x3 NMS test and one shared-memory
-//            atomicMax per cell on a key that encodes the reference's tie-break order:
+//   phase A  a CONSERVATIVE compass pre-test on 6-bit pixels, 8 pixels per thread and iteration.  With q = p >> 2,
+//            p - v > t implies q_p - q_v >= m (m = (t-3)/4 + 1), and a byte lane q_p - q_v + (128 - m) can neither
+//            overflow nor borrow, so "ring point brighter" for 4 pixels is ONE 32-bit add whose byte MSBs are the
+//            flags (darker: the mirrored subtraction).  A pixel survives for polarity bright (dark) iff enough adjacent
+//            compass points (ring 0,4,8,12) pass -- a necessary condition for any arc the LUT accepts, derived from
+//            FAST_N_MIN and verified against the LUT at create time.  Flags of up to 8 row iterations are kept in
+//            registers (one byte lane per pixel, shifted in from the MSB) and emitted ONCE per thread: warp scan of
+//            the counts, one shared-memory atomic per warp, then a find-leading-one loop.  Bright survivors fill the
+//            work list from the front, dark survivors from the back (the position of an entry is its polarity).
+//   phase B  the work list is evaluated densely and EXACTLY for the entry's polarity only: 16 ring bytes packed
+//            4 per word, one packed compare per word, SAD by VABSDIFF4.ACC, the 16 flags merged into one
+//            permuted index of the LUT bitmap.  Hits store their score and go to the positives list.
+//   phase C  the positives list is walked: 3x3 NMS test and one shared-memory atomicMax per cell on a key that
+//            encodes the reference's tie-break order:
 //            (score desc, column priority of the reference's smem tree asc, y-lane (y-y0)%T asc, y asc).
-//  Every pixel rejected in phase A has score 0 in the reference too, so scores are bit-identical.
+//  Every pixel rejected in phase A has score 0 in the reference too; phase B is the reference's arithmetic
+//  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
+//  dense, exact evaluation of the whole tile.
 // =================================================================================================
+#define JSFE_FAST_PW 224   // shared-memory pitch of the pixel tile = TMA box width: covers floor16 slack 15 + 4 + 192 + 4 (+ pad)
 
 // per-byte MSB = (a > b), unsigned bytes; nb7 = ~b & 0x7f7f7f7f (hoisted when b is loop-invariant)
 __device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b, unsigned nb7) {
@@ -159,15 +168,94 @@ __device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b, unsigned nb7)
     return (a & ~b) | (~(a ^ b) & t);
 }
 
-// gathers bit 7 of the 4 bytes of `msbs` (already masked with 0x80808080) into bits 28..31 (byte k -> bit 28+k):
-// the multiplier 2^21 + 2^14 + 2^7 + 1 moves bit 8k+7 to 28+k and no two partial products collide, so there are no carries
-__device__ __forceinline__ unsigned top_nibble_of_msbs(unsigned msbs) { return msbs * 0x00204081u; }
+__device__ __forceinline__ unsigned q6(unsigned w) { return (w >> 2) & 0x3f3f3f3fu; }   // 4 pixels -> 4 six-bit lanes
 
+// (a & ~mask) | (b & mask) as ONE LOP3 (nvcc splits the two-constant form into two)
+__device__ __forceinline__ unsigned bitsel(unsigned a, unsigned b, unsigned mask) {
+    unsigned r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(r) : "r"(a), "r"(b), "r"(mask));
+    return r;
+}
+__device__ __forceinline__ unsigned xor_forced(unsigned a, unsigned m) {   // keeps nvcc from turning x ^ (c ? ~0 : 0) into NOT + SEL
+    unsigned r;
+    asm("xor.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(m));
+    return r;
+}
+// a * b + c on the FMA pipe (IMAD): byte packing there instead of PRMT keeps the ALU pipe, the kernel's limiter, free
+__device__ __forceinline__ unsigned imad(unsigned a, unsigned b, unsigned c) {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned pack4(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {   // b0 | b1 << 8 | b2 << 16 | b3 << 24
+    return imad(imad(b3, 256u, b2), 65536u, imad(b1, 256u, b0));
+}
+// shared-memory atomic add without nvcc's warp-aggregation preamble (the callers already elect one lane)
+__device__ __forceinline__ unsigned atom_add_shared(unsigned* addr, unsigned v) {
+    unsigned r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return r;
+}
+
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned acc) {    // acc + sum of |a_k - b_k| over the 4 bytes
+    unsigned r;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
+    return r;
+}
+
+// phase B for ONE work-list entry: exact FAST decision of ONE polarity (DARK = 0: ring point brighter than v + t, 1: darker than
+// v - t) for the pixel whose centre byte c points at in the staged tile (pitch JSFE_FAST_PW); returns the SAD score or 0.
+// The bytes are packed 4 ring points per word with IMADs (FMA pipe; the ALU pipe is this kernel's limiter), compared with one
+// packed compare per word against the saturated bound (p > min(v+t,255), resp. p < max(v-t,0): saturation never changes the
+// outcome), and the 16 flags are merged into one index of the permuted LUT bitmap.
+template <int DARK>
+__device__ __forceinline__ unsigned fast_eval(const uint8_t* __restrict__ c, int threshold, int compass_mode, const uint32_t* __restrict__ lutp) {
+    constexpr int PW = JSFE_FAST_PW;
+    const int v = c[0];
+    // ring point k -> byte k%4 of word k/4   (offsets: orb_FAST_compute_score.cu:24-48)
+    const unsigned R0 = pack4(c[3 * PW], c[3 * PW + 1], c[2 * PW + 2], c[PW + 3]);
+    const unsigned R1 = pack4(c[3], c[-PW + 3], c[-2 * PW + 2], c[-3 * PW + 1]);
+    const unsigned R2 = pack4(c[-3 * PW], c[-3 * PW - 1], c[-2 * PW - 2], c[-PW - 3]);
+    const unsigned R3 = pack4(c[-3], c[PW - 3], c[2 * PW - 2], c[3 * PW - 1]);
+    unsigned f0, f1, f2, f3;
+    if (DARK) {
+        const unsigned L4 = (unsigned)max(v - threshold, 0) * 0x01010101u, l7 = L4 & 0x7f7f7f7fu;
+        auto lt = [&](unsigned r) { const unsigned t = l7 + (~r & 0x7f7f7f7fu); return (L4 & ~r) | (~(L4 ^ r) & t); };   // MSB: r < L
+        f0 = lt(R0); f1 = lt(R1); f2 = lt(R2); f3 = lt(R3);
+    } else {
+        const unsigned H4 = (unsigned)min(v + threshold, 255) * 0x01010101u, nH7 = ~H4 & 0x7f7f7f7fu;
+        f0 = msb_gt(R0, H4, nH7); f1 = msb_gt(R1, H4, nH7); f2 = msb_gt(R2, H4, nH7); f3 = msb_gt(R3, H4, nH7);
+    }
+    // merge the 16 flags (byte MSBs) into the high nibbles of one word: byte k = [ring k, 4+k, 8+k, 12+k | garbage]
+    unsigned W = bitsel(f1 >> 1, f0, 0x80808080u);
+    W = bitsel(f2 >> 2, W, 0xC0C0C0C0u);
+    W = bitsel(f3 >> 3, W, 0xE0E0E0E0u);
+    const unsigned u = bitsel(W >> 8, W >> 4, 0x0f0f0f0fu);
+    const unsigned idx = __byte_perm(u, 0u, 0x4420);      // 16-bit index in the permuted bit order of DevTables::lut_perm
+    unsigned hit = (__ldg(lutp + (idx >> 5)) >> (idx & 31u)) & 1u;
+    if (compass_mode < 2) {
+        // arcs shorter than 8 need not cover two adjacent compass points: apply the reference's early-outs explicitly
+        // (orb_FAST_compute_score.cu:1452-1470): (4 and 12 both similar) or (0 and 8 both similar) -> score 0
+        const int p0 = (int)(R0 & 255u), p4 = (int)(R1 & 255u), p8 = (int)(R2 & 255u), p12 = (int)(R3 & 255u);
+        const bool d0 = abs(p0 - v) > threshold, d4 = abs(p4 - v) > threshold, d8 = abs(p8 - v) > threshold, d12 = abs(p12 - v) > threshold;
+        if (!((d4 || d12) && (d0 || d8))) hit = 0u;
+    }
+    if (!hit) return 0u;
+    const unsigned V4 = (unsigned)v * 0x01010101u;
+    return sad4_acc(R3, V4, sad4_acc(R2, V4, sad4_acc(R1, V4, sad4_acc(R0, V4, 0u))));
+}
+
+// MODE = Params::compass_mode (0..3), HAS_MASK = the handle has a mask image: compile-time so that the 8-pixel loop carries
+// neither the other modes' predicated-off formulas nor the mask pointer bookkeeping
+template <int MODE, bool HAS_MASK>
 __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_best[192];
-    __shared__ int s_ncand, s_npos;
+    __shared__ unsigned s_ncand;      // work-list counters, packed: bright | dark << 16
+    __shared__ __align__(16) int s_npos[8];   // positives per warp (each warp owns an eighth of the positives area: no atomics, and
+                                              // phase C walks a warp's own segment); -1 = that segment overflowed
+    constexpr int PW = JSFE_FAST_PW;
     const uint32_t item = __ldg(p.fast_map + blockIdx.x);   // level << 28 | tile row << 14 | block in row
     const int l = (int)(item >> 28);
     const LevelGeom& lv = p.lv[l];
@@ -178,16 +266,21 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int X0 = tx0 * lv.tile_w, GW = ncells * lv.tile_w, y0 = ty * lv.tile_h;
     const int gx0 = ((X0 - 4) >> 4) << 4, gy0 = y0 - 4;
     const int PR = lv.tile_h + 8;
-    const int PW = lv.tile_pw;          // fixed per level (= TMA box width); covers X0+GW+4-gx0 for every block
     const int SW = (GW + 2 + 7) & ~7;   // score row length (u16), multiple of 8 -> rows are 16-byte aligned
     const int SR = lv.tile_h + 2;
+    const int cs0 = X0 - 1 - gx0;       // tile column of score column 0
     uint8_t* pix = smem;
     uint16_t* sc = reinterpret_cast<uint16_t*>(smem + (size_t)PR * PW);
-    uint16_t* cand = sc + (size_t)SR * SW;           // work list of codes (score row << 8 | score column)
-    uint16_t* pos = cand + (size_t)SR * SW;          // positives list (capacity = a quarter of the work list)
-    const int pos_cap = (SR * SW) >> 2;
+    // work list of codes (score row << 8 | score column), one slot per score position: bright survivors from the front, dark ones
+    // from the back (a position can be in both); the gap in between later holds the positives.  cap < capf only in overflow tests.
+    uint16_t* cand = sc + (size_t)SR * SW;
+    const int capf = SR * SW;
+    const int cap = p.fast_list_cap > 0 ? min(p.fast_list_cap, capf) : capf;
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
+    // pixels whose score can be non-zero: interior [B, w-B) x [B, h-B) (score positions of this block: rows ry, columns rx)
+    const int ry_lo = max(0, JSFE_B - (y0 - 1)), ry_hi = min(SR, lv.h - JSFE_B - (y0 - 1));
+    const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
 
     // ---- stage the pixel tile: one TMA box load (out-of-image rows/columns arrive as 0); meanwhile clear the scores
     if (p.use_tma) {
@@ -197,7 +290,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
             tma_load_3d(pix, &tm.tile[l], &s_bar, gx0, gy0, slot);
         }
     } else {
-        const int vpr = PW >> 4, nvec = PR * vpr;
+        constexpr int vpr = PW >> 4;
+        const int nvec = PR * vpr;
         for (int i = tid; i < nvec; i += 256) {
             const int row = i / vpr, v = i - row * vpr;
             const int gy = gy0 + row, gx = gx0 + (v << 4);
@@ -212,193 +306,204 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         const int nz = (SR * SW) >> 3;
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < 192) s_best[tid] = 0;
-        if (tid == 0) {
-            s_ncand = 0;
-            s_npos = 0;
-        }
+        if (tid == 0) s_ncand = 0;
     }
     __syncthreads();                      // also makes the mbarrier init visible to every thread
     if (p.use_tma) mbar_wait(&s_bar, 0);  // TMA bytes have landed
 
-    // ---- phase A: compass pre-test, 8 pixels (two 32-bit words) per thread and iteration;
-    //      thread = (column group g, row lane rl) on the level's fixed ngx x nrl grid; survivors go to the work list
+    // ---- phase A: conservative compass pre-test on 6-bit pixels; thread = (column group g, row lane rl) on the level's
+    //      fixed ngx x nrl grid, 8 pixels (two 32-bit words) per iteration, up to 8 iterations between two emissions
     {
-        const int cs0 = X0 - 1 - gx0;               // smem column of score column 0
         const int g0 = cs0 >> 3;                    // first 8-pixel column group that holds a score column
         const int nrl = lv.fast_nrl;
-        // score rows whose y lies in the interior [B, h-B): ry in [ry_lo, ry_hi)
-        const int ry_lo = max(0, JSFE_B - (y0 - 1)), ry_hi = min(SR, lv.h - JSFE_B - (y0 - 1));
         const int rl = (int)(((unsigned)tid * lv.fast_ngx_inv) >> 16), g = tid - rl * lv.fast_ngx;
         const int c = (g0 + g) << 3, xb = gx0 + c;
-        const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
-        // column validity masks of this thread's 2 x 4 pixels (MSB per byte), hoisted out of the row loop:
-        // bytes [lo, hi) of the 8-byte group are valid
-        unsigned vma = 0, vmb = 0;
+        // column validity of this thread's 2 x 4 pixels (0xFF per valid byte), hoisted out of the row loop
+        unsigned vxa = 0, vxb = 0;
         {
             const int lo = min(max(xlo - xb, 0), 8), hi = min(max(xhi - xb + 1, 0), 8);
             if (hi > lo && rl < nrl) {
-                const unsigned long long ones = 0x8080808080808080ull;
-                const unsigned long long m = (hi == 8 ? ones : (ones & ((1ull << (8 * hi)) - 1ull))) & ~((1ull << (8 * lo)) - 1ull);
-                vma = (unsigned)m;
-                vmb = (unsigned)(m >> 32);
+                const unsigned long long m = (hi == 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull)) & ~((1ull << (8 * lo)) - 1ull);
+                vxa = (unsigned)m;
+                vxb = (unsigned)(m >> 32);
             }
         }
-        const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
-        const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
-        const int mode = p.compass_mode;
-        const unsigned lt = (1u << lane) - 1u;
+        const unsigned C4 = (unsigned)(128 - p.fast_q_thresh) * 0x01010101u;
         int ry = ry_lo + rl;
         const uint8_t* rp = pix + (ry + 3) * PW + c;
-        const uint8_t* mp = lv.mask ? lv.mask + (size_t)(y0 - 1 + ry) * lv.pitch + xb : nullptr;
-        int code0 = (ry << 8) + (c - cs0);          // work-list code of this thread's first pixel
+        const uint8_t* mp = HAS_MASK ? lv.mask + (size_t)(y0 - 1 + ry) * lv.pitch + xb : nullptr;
         const int rstep = nrl * PW, cstep = nrl << 8;
         const size_t mstep = (size_t)nrl * lv.pitch;
-        // one 4-pixel group: v = centre pixels, P0/P8 = rows +3/-3, P4/P12 = columns +3/-3
-        auto compass = [&](unsigned v, unsigned P0, unsigned P4, unsigned P8, unsigned P12) -> unsigned {
-            const unsigned nv7 = ~v & 0x7f7f7f7fu;
-            const unsigned df0 = msb_gt(__vabsdiffu4(P0, v), T4, nT7), gt0 = msb_gt(P0, v, nv7);
-            const unsigned df4 = msb_gt(__vabsdiffu4(P4, v), T4, nT7), gt4 = msb_gt(P4, v, nv7);
-            const unsigned df8 = msb_gt(__vabsdiffu4(P8, v), T4, nT7), gt8 = msb_gt(P8, v, nv7);
-            const unsigned df12 = msb_gt(__vabsdiffu4(P12, v), T4, nT7), gt12 = msb_gt(P12, v, nv7);
-            // reference early-outs: (4 and 12 both similar) or (0 and 8 both similar) -> score 0
-            const unsigned keep = (df4 | df12) & (df0 | df8);
-            unsigned cond;
-            if (mode == 2) {         // an arc of >= 8 covers two ADJACENT compass points: one of {0,8} and one of {4,12}
-                cond = (((df0 & gt0) | (df8 & gt8)) & ((df4 & gt4) | (df12 & gt12))) |
-                       (((df0 & ~gt0) | (df8 & ~gt8)) & ((df4 & ~gt4) | (df12 & ~gt12)));
-            } else if (mode == 3) {  // three adjacent compass points
-                const unsigned b0 = df0 & gt0, b4 = df4 & gt4, b8 = df8 & gt8, b12 = df12 & gt12;
-                const unsigned k0 = df0 & ~gt0, k4 = df4 & ~gt4, k8 = df8 & ~gt8, k12 = df12 & ~gt12;
-                cond = (b0 & b4 & b8) | (b4 & b8 & b12) | (b8 & b12 & b0) | (b12 & b0 & b4) |
-                       (k0 & k4 & k8) | (k4 & k8 & k12) | (k8 & k12 & k0) | (k12 & k0 & k4);
-            } else if (mode == 1) {
-                cond = df0 | df4 | df8 | df12;
-            } else {
-                cond = 0xffffffffu;
+        // one 4-pixel group on 6-bit lanes: V = centre pixels, P0/P8 = rows +3/-3, P4/P12 = columns +3/-3.  Returns the
+        // bright flags in fb and the dark flags in fd (byte MSBs; other bits are garbage)
+        auto compass = [&](unsigned V, unsigned P0, unsigned P4, unsigned P8, unsigned P12, unsigned& fb, unsigned& fd) {
+            const unsigned A = C4 - V, B = C4 + V;
+            const unsigned b0 = P0 + A, b4 = P4 + A, b8 = P8 + A, b12 = P12 + A;       // MSB: q_p - q_v >= m
+            const unsigned d0 = B - P0, d4 = B - P4, d8 = B - P8, d12 = B - P12;       // MSB: q_v - q_p >= m
+            if (MODE == 2) {         // an arc of >= 8 covers two ADJACENT compass points: one of {0,8} and one of {4,12}
+                fb = (b0 | b8) & (b4 | b12);
+                fd = (d0 | d8) & (d4 | d12);
+            } else if (MODE == 3) {  // three adjacent compass points = at least three of the four
+                fb = (b0 & b8 & (b4 | b12)) | (b4 & b12 & (b0 | b8));
+                fd = (d0 & d8 & (d4 | d12)) | (d4 & d12 & (d0 | d8));
+            } else {                 // no usable arc condition: only the reference's two early-outs, either polarity
+                fb = fd = ((b4 | d4) | (b12 | d12)) & ((b0 | d0) | (b8 | d8));
             }
-            return cond & keep & 0x80808080u;
         };
-        // block-uniform trip count (the list append is warp-collective)
-        for (int ry0 = ry_lo; ry0 < ry_hi; ry0 += nrl, ry += nrl, rp += rstep, code0 += cstep) {
-            unsigned pa = 0, pb = 0;
-            if ((vma | vmb) && ry < ry_hi) {
-                const unsigned W0 = *reinterpret_cast<const unsigned*>(rp - 4);
-                const uint2 W12 = *reinterpret_cast<const uint2*>(rp);          // c is a multiple of 8
-                const unsigned W3 = *reinterpret_cast<const unsigned*>(rp + 8);
-                const uint2 D = *reinterpret_cast<const uint2*>(rp + 3 * PW);    // ring 0  (0,+3)
-                const uint2 U = *reinterpret_cast<const uint2*>(rp - 3 * PW);    // ring 8  (0,-3)
-                pa = compass(W12.x, D.x, __byte_perm(W12.x, W12.y, 0x6543), U.x, __byte_perm(W0, W12.x, 0x4321)) & vma;
-                pb = compass(W12.y, D.y, __byte_perm(W12.y, W3, 0x6543), U.y, __byte_perm(W12.x, W12.y, 0x4321)) & vmb;
-                if (mp != nullptr) {
-                    const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mp));
-                    pa &= msb_gt(mw.x, 0u, 0x7f7f7f7fu);
-                    pb &= msb_gt(mw.y, 0u, 0x7f7f7f7fu);
+        for (int r0 = ry_lo; r0 < ry_hi; r0 += 8 * nrl) {    // block-uniform trip counts (the emission is warp-collective)
+            const int nit = min(8, (ry_hi - r0 + nrl - 1) / nrl);
+            const int code_first = (ry << 8) + (c - cs0);     // work-list code of this thread's first pixel in this chunk
+            unsigned aba = 0, abb = 0, ada = 0, adb = 0;      // flag accumulators: byte lane = pixel, newest iteration in the MSB
+            for (int it = 0; it < nit; ++it, ry += nrl, rp += rstep) {
+                unsigned fba = 0, fbb = 0, fda = 0, fdb = 0;
+                if ((vxa | vxb) && ry < ry_hi) {
+                    const unsigned Q0 = q6(*reinterpret_cast<const unsigned*>(rp - 4));
+                    const uint2 W12 = *reinterpret_cast<const uint2*>(rp);          // c is a multiple of 8
+                    const unsigned Q3 = q6(*reinterpret_cast<const unsigned*>(rp + 8));
+                    const uint2 D = *reinterpret_cast<const uint2*>(rp + 3 * PW);    // ring 0  (0,+3)
+                    const uint2 U = *reinterpret_cast<const uint2*>(rp - 3 * PW);    // ring 8  (0,-3)
+                    const unsigned Q1 = q6(W12.x), Q2 = q6(W12.y);
+                    compass(Q1, q6(D.x), __byte_perm(Q1, Q2, 0x6543), q6(U.x), __byte_perm(Q0, Q1, 0x4321), fba, fda);
+                    compass(Q2, q6(D.y), __byte_perm(Q2, Q3, 0x6543), q6(U.y), __byte_perm(Q1, Q2, 0x4321), fbb, fdb);
+                    if (HAS_MASK) {
+                        const uint2 mw = __ldg(reinterpret_cast<const uint2*>(mp));
+                        const unsigned ma = msb_gt(mw.x, 0u, 0x7f7f7f7fu), mb = msb_gt(mw.y, 0u, 0x7f7f7f7fu);
+                        fba &= ma; fda &= ma; fbb &= mb; fdb &= mb;
+                    }
                 }
+                if (HAS_MASK) mp += mstep;
+                aba = bitsel(aba >> 1, fba, 0x80808080u);
+                abb = bitsel(abb >> 1, fbb, 0x80808080u);
+                ada = bitsel(ada >> 1, fda, 0x80808080u);
+                adb = bitsel(adb >> 1, fdb, 0x80808080u);
             }
-            if (mp != nullptr) mp += mstep;
-            // append survivors to the work list: exclusive prefix of the per-lane count (0..8) from 4 ballots
-            const unsigned cnt = (((pa >> 7) + (pb >> 7)) * 0x01010101u) >> 24;
-            const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u);
-            const unsigned c1 = __ballot_sync(0xffffffffu, cnt & 2u);
-            const unsigned c2 = __ballot_sync(0xffffffffu, cnt & 4u);
-            const unsigned c3 = __ballot_sync(0xffffffffu, cnt & 8u);
-            if (c0 | c1 | c2 | c3) {
-                const int pre = __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt) + 8 * __popc(c3 & lt);
-                int base = pre + (int)cnt;                 // lane 31 holds the warp total
-                base = __shfl_sync(0xffffffffu, base, 31);
-                if (lane == 0) base = atomicAdd(&s_ncand, base);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                uint16_t* o = cand + base + pre;
-                if (pa & 0x00000080u) *o++ = (uint16_t)code0;
-                if (pa & 0x00008000u) *o++ = (uint16_t)(code0 + 1);
-                if (pa & 0x00800000u) *o++ = (uint16_t)(code0 + 2);
-                if (pa & 0x80000000u) *o++ = (uint16_t)(code0 + 3);
-                if (pb & 0x00000080u) *o++ = (uint16_t)(code0 + 4);
-                if (pb & 0x00008000u) *o++ = (uint16_t)(code0 + 5);
-                if (pb & 0x00800000u) *o++ = (uint16_t)(code0 + 6);
-                if (pb & 0x80000000u) *o = (uint16_t)(code0 + 7);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: full ring evaluation of the survivors, dense, 4 ring points per packed word
-    const int ncand = s_ncand;
-    {
-        const uint32_t* __restrict__ lut = p.tab->lut_bits;
-        const unsigned T4 = (unsigned)p.threshold * 0x01010101u;
-        const unsigned nT7 = ~T4 & 0x7f7f7f7fu;
-        const int cs0 = X0 - 1 - gx0;
-        const int nit = (ncand + 255) >> 8;       // warp-uniform trip count: the positives append is warp-collective
-        for (int it = 0, i = tid; it < nit; ++it, i += 256) {
-            unsigned score = 0;
-            int idx = 0;
-          if (i < ncand) {
-            idx = cand[i];
-            const int ry = idx >> 8, rx = idx & 255;
-            const uint8_t* c = pix + (ry + 3) * PW + (cs0 + rx);
-            const unsigned V = (unsigned)c[0] * 0x01010101u, nV7 = ~V & 0x7f7f7f7fu;
-            // ring point k -> byte k%4 of word k/4   (offsets: orb_FAST_compute_score.cu:24-48)
-            const unsigned R0 = __byte_perm(__byte_perm(c[3 * PW], c[3 * PW + 1], 0x0040), __byte_perm(c[2 * PW + 2], c[PW + 3], 0x0040), 0x5410);
-            const unsigned R1 = __byte_perm(__byte_perm(c[3], c[-PW + 3], 0x0040), __byte_perm(c[-2 * PW + 2], c[-3 * PW + 1], 0x0040), 0x5410);
-            const unsigned R2 = __byte_perm(__byte_perm(c[-3 * PW], c[-3 * PW - 1], 0x0040), __byte_perm(c[-2 * PW - 2], c[-PW - 3], 0x0040), 0x5410);
-            const unsigned R3 = __byte_perm(__byte_perm(c[-3], c[PW - 3], 0x0040), __byte_perm(c[2 * PW - 2], c[3 * PW - 1], 0x0040), 0x5410);
-            unsigned bright = 0, dark = 0, sad = 0;
+            // emission: the flag of iteration `it` sits at bit 8 - nit + it of its pixel's byte lane
+            aba &= vxa; abb &= vxb; ada &= vxa; adb &= vxb;
+            const int cb = __popc(aba) + __popc(abb), cd = __popc(ada) + __popc(adb);
+            unsigned incl = (unsigned)cb | ((unsigned)cd << 16);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned R = q == 0 ? R0 : q == 1 ? R1 : q == 2 ? R2 : R3;
-                sad = __vsadu4(R, V) + sad;
-                const unsigned df = msb_gt(__vabsdiffu4(R, V), T4, nT7), gt = msb_gt(R, V, nV7);
-                // ring points 4q..4q+3 enter at bits 28..31; after 4 words the 16 flags sit in bits 16..31, ring 0 lowest
-                bright = (bright >> 4) | (top_nibble_of_msbs(df & gt & 0x80808080u) & 0xF0000000u);
-                dark = (dark >> 4) | (top_nibble_of_msbs(df & ~gt & 0x80808080u) & 0xF0000000u);
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += n;
             }
-            bright >>= 16;
-            dark >>= 16;
-            const unsigned hit = ((__ldg(lut + (bright >> 5)) >> (bright & 31)) | (__ldg(lut + (dark >> 5)) >> (dark & 31))) & 1u;
-            score = hit ? sad : 0u;
-            sc[ry * SW + rx] = (uint16_t)score;
-          }
-            // positives (about 40 % of the candidates) go to a second, smaller list so that phase C runs dense
-            const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);
-            if (pb) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_npos, __popc(pb));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int o = base + __popc(pb & ((1u << lane) - 1u));
-                if (score != 0u && o < pos_cap) pos[o] = (uint16_t)idx;
+            const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (tot) {
+                unsigned base = 0;
+                if (lane == 31) base = atom_add_shared(&s_ncand, tot);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                int ob = (int)((base & 0xffffu) + (incl & 0xffffu)) - cb;     // first bright slot of this thread
+                int od = (int)((base >> 16) + (incl >> 16)) - cd;            // first dark slot (counted from the back)
+                const int code_base = code_first - (8 - nit) * cstep;
+                auto emit = [&](unsigned m, int col_off, int& o, bool from_back) {
+                    while (m) {
+                        const int b = 31 - __clz((int)m);
+                        m ^= 1u << b;
+                        const int code = code_base + (b & 7) * cstep + (b >> 3) + col_off;
+                        cand[from_back ? capf - 1 - o : o] = (uint16_t)code;    // o < capf: at most one entry per position and polarity
+                        ++o;
+                    }
+                };
+                emit(aba, 0, ob, false);
+                emit(abb, 4, ob, false);
+                emit(ada, 0, od, true);
+                emit(adb, 4, od, true);
             }
         }
     }
     __syncthreads();
 
-    // ---- phase C: NMS + per-cell arg-max over the work list
+    // ---- phase B: exact evaluation of the work list (one polarity per entry); hits store their score and join the positives.
+    //      The positives of warp w go to its eighth of the gap between the bright and the dark entries: positives <= entries
+    //      evaluated, so the gap cannot overflow while the work list is at most half full.
+    const unsigned ncand2 = s_ncand;
+    const int nb = (int)(ncand2 & 0xffffu), nd = (int)(ncand2 >> 16), ntot = nb + nd;
+    const bool list_ok = ntot <= cap;
+    const int pos_seg = list_ok ? (p.fast_list_cap > 0 ? min(p.fast_list_cap, (capf - ntot) >> 3) : (capf - ntot) >> 3) : 0;
+    uint16_t* pos = cand + nb + (tid >> 5) * pos_seg;       // this warp's segment
+    {
+        const uint32_t* __restrict__ lutp = p.tab->lut_perm;
+        const uint8_t* cbase = pix + 3 * PW + cs0;
+        if (list_ok) {
+            const int nit = (ntot + 255) >> 8;        // warp-uniform trip count: the positives append is warp-collective
+            const unsigned lt = (1u << lane) - 1u;
+            int wpos = 0;                              // positives of this warp so far (warp-uniform)
+            for (int it = 0, i = tid; it < nit; ++it, i += 256) {
+                unsigned score = 0;
+                int code = 0;
+                const int w0 = i - lane;              // first entry of this warp: the polarity is warp-uniform except in one warp per block
+                if (w0 + 31 < nb) {
+                    code = cand[i];
+                    score = fast_eval<0>(cbase + (code >> 8) * PW + (code & 255), p.threshold, MODE, lutp);
+                } else if (w0 >= nb) {
+                    if (i < ntot) {
+                        code = cand[capf - 1 - (i - nb)];
+                        score = fast_eval<1>(cbase + (code >> 8) * PW + (code & 255), p.threshold, MODE, lutp);
+                    }
+                } else if (i < ntot) {
+                    const bool dark = i >= nb;
+                    code = cand[dark ? capf - 1 - (i - nb) : i];
+                    const uint8_t* c = cbase + (code >> 8) * PW + (code & 255);
+                    score = dark ? fast_eval<1>(c, p.threshold, MODE, lutp) : fast_eval<0>(c, p.threshold, MODE, lutp);
+                }
+                if (score) sc[(code >> 8) * SW + (code & 255)] = (uint16_t)score;
+                const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);
+                const int o = wpos + __popc(pb & lt);
+                if (score != 0u && o < pos_seg) pos[o] = (uint16_t)code;
+                wpos += __popc(pb);
+            }
+            if (lane == 0) s_npos[tid >> 5] = wpos <= pos_seg ? wpos : -1;
+        } else {
+            // work list overflow (more survivors than score positions: adversarial input): every interior pixel, both polarities
+            const int n = SR * SW;
+            if (lane == 0) s_npos[tid >> 5] = -1;
+            for (int i = tid; i < n; i += 256) {
+                const int ry = i / SW, rx = i - ry * SW;
+                const int x = X0 - 1 + rx;
+                if (ry < ry_lo || ry >= ry_hi || x < xlo || x > xhi) continue;
+                if (HAS_MASK && lv.mask[(size_t)(y0 - 1 + ry) * lv.pitch + x] == 0) continue;
+                const uint8_t* c = cbase + ry * PW + rx;
+                unsigned score = fast_eval<0>(c, p.threshold, MODE, lutp);
+                if (!score) score = fast_eval<1>(c, p.threshold, MODE, lutp);
+                if (score) sc[i] = (uint16_t)score;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: NMS + per-cell arg-max.  Every warp walks its own positives; if any segment overflowed (or the work list did),
+    //      the whole score tile is walked instead (exact, slower: noise-like or adversarial tiles only)
     {
         const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
         const int wv = min(GW, lv.w - X0);          // owned columns actually inside the image
-        const int npos = s_npos;
-        const bool dense = npos <= pos_cap;          // else: noise-like tile, walk the candidate list instead
-        const uint16_t* list = dense ? pos : cand;
-        const int nlist = dense ? npos : ncand;
-        for (int i = tid; i < nlist; i += 256) {
-            const int code = list[i];
-            const int ry = code >> 8, rx = code & 255;
+        // one candidate: 3x3 NMS (ties survive) and the packed arg-max key of its cell
+        auto nms = [&](int ry, int rx, unsigned s) {
+            const int dy = ry - 1, xx = rx - 1, y = y0 + dy;
             const uint16_t* row = sc + ry * SW + rx;
-            const unsigned s = row[0];
-            if (s) {
-                const int dy = ry - 1, xx = rx - 1, y = y0 + dy;
-                if (y >= ymin && y < ymax && xx >= 0 && xx < wv) {
-                    const uint16_t* up = row - SW;
-                    const uint16_t* dn = row + SW;
-                    const bool ok = s >= up[-1] && s >= up[0] && s >= up[1] && s >= row[-1] && s >= row[1] &&
-                                    s >= dn[-1] && s >= dn[0] && s >= dn[1];
-                    if (ok) {
-                        const unsigned ck = __ldg(&p.tab->colkey[l][xx]);
-                        const unsigned key = (s << 18) | ((ck >> 8) << 11) | (unsigned)__ldg(&p.tab->rowkey[l][dy]);
-                        atomicMax(&s_best[ck & 0xFFu], key);
-                    }
-                }
+            const uint16_t* up = row - SW;
+            const uint16_t* dn = row + SW;
+            const unsigned m = max(max(max((unsigned)up[-1], (unsigned)up[0]), max((unsigned)up[1], (unsigned)row[-1])),
+                                   max(max((unsigned)row[1], (unsigned)dn[-1]), max((unsigned)dn[0], (unsigned)dn[1])));
+            if (s >= m && y >= ymin && y < ymax && xx >= 0 && xx < wv) {
+                const unsigned ck = __ldg(&p.tab->colkey[l][xx]);
+                const unsigned key = (s << 18) | ((ck >> 8) << 11) | (unsigned)__ldg(&p.tab->rowkey[l][dy]);
+                atomicMax(&s_best[ck & 0xFFu], key);
             }
+        };
+        const int4 na = *reinterpret_cast<const int4*>(s_npos), nb4 = *reinterpret_cast<const int4*>(s_npos + 4);
+        const bool dense = (na.x | na.y | na.z | na.w | nb4.x | nb4.y | nb4.z | nb4.w) >= 0;
+        if (dense) {
+            const int npos = s_npos[tid >> 5];
+            for (int i = lane; i < npos; i += 32) {
+                const int code = pos[i];
+                const int ry = code >> 8, rx = code & 255;     // a positive: score > 0, row and column >= 1 by construction of phase A
+                nms(ry, rx, sc[ry * SW + rx]);
+            }
+        } else {
+            for (int ry = 1 + (tid >> 5); ry < SR - 1; ry += 8)       // warp = row, lane = column: no division
+                for (int rx = 1 + lane; rx < SW - 1; rx += 32) {
+                    const unsigned s = sc[ry * SW + rx];
+                    if (s) nms(ry, rx, s);
+                }
         }
     }
     __syncthreads();

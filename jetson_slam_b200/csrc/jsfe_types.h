@@ -21,7 +21,7 @@ struct LevelGeom {
     int tile_row_offset;             // running sum of n_tile_h (index into row_start)
     int T;                           // y-lanes of the reference's NMS launch (tie-break rule)
     int cells_per_block;             // NMS cells one k_fast_cells block owns (adjacent in a tile row)
-    int tile_pw;                     // shared-memory pixel-tile pitch of k_fast_cells = TMA box width (multiple of 16)
+    int tile_pw;                     // shared-memory pixel-tile pitch of k_fast_cells = TMA box width (JSFE_FAST_PW for every level)
     int blocks_per_row;              // ceil(n_tile_w / cells_per_block)
     int block_offset;                // first k_fast_cells work item of this level
     int fast_ngx, fast_nrl;          // k_fast_cells phase A thread grid: 8-pixel column groups x row lanes (ngx*nrl <= 256)
@@ -39,6 +39,8 @@ struct LevelGeom {
 // Small read-only tables in global memory (one copy per handle).
 struct DevTables {
     uint32_t lut_bits[2048];   // FAST arc LUT, 1 bit per 16-bit ring mask; bit 0xFFFF = 0
+    uint32_t lut_perm[2048];   // the same LUT indexed by k_fast_cells' merged flag word: ring point 4j+k is index bit perm(j,k)
+                               // (byte k of ring word j): k=0 -> bits 3..0, k=1 -> 7..4, k=2 -> 11..8, k=3 -> 15..12, j=0 highest
     int umax[16];              // radius-15 disc half-widths
     float gauss[49];           // 7x7 sigma=10 weights, row-major
     float sep_a[7], sep_b[7];  // separable factors: gauss[i*7+j] ~= sep_a[i]*sep_b[j] (|err| < 4e-9)
@@ -60,6 +62,8 @@ struct Params {
     unsigned long long vmax_packed;  // nibble |u| (0..15) = largest |v| of the radius-15 disc whose row contains column u
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
     int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
+    int fast_q_thresh; // k_fast_cells phase A: m = (t-3)/4 + 1 (0 for t < 3): p - v > t implies (p>>2) - (v>>2) >= m
+    int fast_list_cap; // 0 = work list holds every score position; > 0 (JSFE_DEBUG_FAST_CAP): forced small lists (overflow tests)
     int H0, W0;
     int pyr_blocks_total;             // k_pyramid blocks (128x32 pixel tiles) over levels 1..L-1
     int pyr_block_start[JSFE_MAXL + 1];
@@ -90,7 +94,7 @@ struct Params {
 };
 
 // TMA descriptors (cuTensorMapEncodeTiled, 3-D u8 tensors {pitch, h, slots}), passed as one __grid_constant__ parameter.
-//   tile[l]: box {tile_pw[l], tile_h+8, 1} of level l       -> k_fast_cells pixel tile (+4 px halo), out-of-image = 0
+//   tile[l]: box {JSFE_FAST_PW, tile_h+8, 1} of level l     -> k_fast_cells pixel tile (+4 px halo), out-of-image = 0
 //   disc[l]: box {48, 31, 1} of level l                      -> k_orient_desc intensity-centroid disc
 //   win[l] : box {64, 37, 1} of the BLURRED level l          -> k_orient_desc rBRIEF sample window
 // Box origins must be 16-byte aligned in x (u8 elements): an unaligned innermost coordinate traps (measured on B200).

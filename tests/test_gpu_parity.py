@@ -96,6 +96,38 @@ def test_other_arc_bands_match_oracle(n_min, n_max, th):
     fe.close()
 
 
+@pytest.mark.parametrize("cap", [1, 40, 700])
+@pytest.mark.parametrize("kind", ["synthetic", "noise", "checker"])
+def test_fast_list_overflow_paths_stay_exact(cap, kind, monkeypatch):
+    """k_fast_cells keeps its survivors in fixed-size shared-memory lists.  JSFE_DEBUG_FAST_CAP shrinks them so that the overflow
+    paths run (work list: dense evaluation of the tile, both polarities; positives: dense NMS walk); results must not change.
+    Noise and checkerboard images also put survivors of BOTH polarities next to each other."""
+    import dataclasses
+    cfg = dataclasses.replace(CONFIGS["C1"], th_fast_max=12)
+    if kind == "synthetic":
+        img = synth.stereo_pair(cfg.height, cfg.width, 9)[0]
+    elif kind == "noise":
+        img = np.random.default_rng(3).integers(0, 256, size=(cfg.height, cfg.width), dtype=np.uint8)
+    else:
+        yy, xx = np.mgrid[0:cfg.height, 0:cfg.width]
+        img = (((yy // 3 + xx // 3) % 2) * 200 + 20 + (yy * 7 + xx * 13) % 5).astype(np.uint8)
+    o = orc.Oracle(**cfg.extractor_kwargs())
+    wk, wd = o.extract(img)
+    ox, oy, os_ = o.cells()
+    monkeypatch.setenv("JSFE_DEBUG_FAST_CAP", str(cap))
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=1)
+    monkeypatch.delenv("JSFE_DEBUG_FAST_CAP")
+    fe.set_images(img[None])
+    fe.extract(0, 1)
+    cx, cy, cs = fe.cells(0)
+    assert np.array_equal(cs, os_), f"cell scores: {np.count_nonzero(cs != os_)} differ"
+    pos = os_ > 0
+    assert np.array_equal(cx[pos], ox[pos]) and np.array_equal(cy[pos], oy[pos])
+    kps, desc = fe.get_keypoints(0)
+    assert np.array_equal(kps, wk) and np.array_equal(desc, wd)
+    fe.close()
+
+
 def _random_geometry(i):
     rng = np.random.default_rng(1000 + i)
     h, w = int(rng.integers(70, 420)), int(rng.integers(70, 520))
@@ -215,6 +247,29 @@ def test_batch_slots_are_independent_and_order_invariant():
             if s_ % 2 == 0:
                 assert np.array_equal(e["u_right"][s_, :n].view(np.int32), want["u_right"][s_, :n].view(np.int32))
                 assert np.array_equal(e["depth"][s_, :n].view(np.int32), want["depth"][s_, :n].view(np.int32))
+
+
+def test_chunk_schedule_covers_every_pair_exactly_once():
+    """jsfe_process_host_pairs for every (chunk_pairs, n_pairs) in 1..4 x 1..16: the ramped schedule (C/4, C/2, C ... C/2, C/4) must
+    process exactly the caller's pairs (a schedule that ran past n_pairs would read beyond the host buffer) and give the bytes of
+    the unchunked call."""
+    cfg = CONFIGS["tiny"]
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, 40 + s) for s in range(16)]
+    host = np.stack([im for p in pairs for im in p])
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=32)
+    e = fe.process_host_pairs(host, cfg.mb, cfg.mbf, chunk_pairs=16)
+    want = {k: np.array(v) for k, v in e.items() if k != "bytes"}
+    for chunk in (1, 2, 3, 4):
+        for n in range(1, 17):
+            # the guard page: the buffer handed in ends right after pair n-1
+            e = fe.process_host_pairs(np.ascontiguousarray(host[: 2 * n]), cfg.mb, cfg.mbf, chunk_pairs=chunk)
+            assert np.array_equal(e["n"], want["n"][: 2 * n]), (chunk, n)
+            for s_ in range(2 * n):
+                k = want["n"][s_]
+                assert np.array_equal(e["kps"][s_, :, :k], want["kps"][s_, :, :k]) and np.array_equal(e["desc"][s_, :k], want["desc"][s_, :k]), (chunk, n, s_)
+                if s_ % 2 == 0:
+                    assert np.array_equal(e["u_right"][s_, :k].view(np.int32), want["u_right"][s_, :k].view(np.int32)), (chunk, n, s_)
+    fe.close()
 
 
 def test_single_chunk_graph_replay_tracks_inputs_and_parameters(monkeypatch):
