@@ -12,8 +12,12 @@ then the left<->right Hamming + SAD stereo match) over a batch of `--pairs` synt
 Inputs: 2*pairs images of 1241x376 u8 per GPU per step = 150 MB at the default 160 pairs -> larger than the 126 MB L2,
 so no L2 flush is needed between iterations (config.l2: "inputs>L2").
 Timing: CUDA events on the launching stream, bracketed by barrier + synchronize, max over ranks.
-Multi-GPU: pairs are independent -> one process per GPU, no data-path collective (weak scaling); `--gather` adds the
-NCCL gather of result slabs to rank 0 that a batch consumer would request.
+Multi-GPU: pairs are independent -> one process per GPU, no data-path collective (weak scaling): `value` at N GPUs is that.  For
+N > 1 the same line also carries `gather`: the step with the C ABI's jsfe_gather_* behind it (every rank's results, trimmed to the
+keypoint counts, stored into rank 0's memory over NVLink on a side stream while the next batch is extracted), and `c5_batch_gather`:
+BASELINE configs[4] (1920x1080, one pair per GPU, gathered).
+Parity is asserted in the same run: the results of the timed configuration are compared with the committed reference goldens and with
+the CPU oracle; any mismatch makes the run fail.
 """
 from __future__ import annotations
 
@@ -126,6 +130,84 @@ def ncu_traffic(kernel, units):
         except Exception:
             return None
     return None
+
+
+def workload_config(cfg, pairs_per_gpu):
+    """The workload definition both arms print as `config` (identical keys and values; what a run measured goes elsewhere)."""
+    return {"workload": cfg.name, "height": cfg.height, "width": cfg.width, "n_levels": cfg.n_levels, "tile": cfg.tile_h,
+            "fast_threshold": cfg.th_fast_max, "fast_arc": [cfg.fast_n_min, cfg.fast_n_max], "pairs_per_step_per_gpu": pairs_per_gpu,
+            "l2": "inputs>L2 (%.0f MB of level-0 images per step per GPU)" % (2 * pairs_per_gpu * cfg.height * cfg.width / 1e6)}
+
+
+def pin_to_gpu_numa(index):
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned buffers are allocated (first touch): on the
+    8-GPU box ranks 0-3 sit on node 0 and 4-7 on node 1, and unpinned uploads from the wrong socket cost ~5 % at N = 8."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:   # affinity is an optimisation, never a failure
+        return {"numa_node": None, "note": repr(e)[:80]}
+
+
+def best_cpu_threads(cfg, imgs, fixed=0):
+    """All the host threads the port can USE: with SMT and shared caches the fastest count is often below os.cpu_count(), so try
+    cores, cores/2 and cores/4 on a small sample and keep the best (both arms use this)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if fixed:
+        return max(1, min(cores, fixed)), {}
+    tried = {}
+    for t in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+        cpu_pairs_per_s(cfg, imgs, t, max(1, t // 4))                  # spin the threads up
+        tried[t] = cpu_pairs_per_s(cfg, imgs, t, 2 * t)[0]
+    return max(tried, key=tried.get), tried
+
+
+def check_parity(cfg, pairs_seeds, get_pair, golden_dir, n_oracle=2):
+    """Compare the results of the timed configuration with (1) the committed goldens of the reference's own kernels and (2) the CPU
+    oracle.  get_pair(i) -> dict(kps_l, desc_l, kps_r, desc_r, u_right, depth) for the i-th distinct pair.  -> (checked, mismatches, notes)"""
+    from jetson_slam_b200 import synth
+    from oracle import oracle as orc
+    checked, bad, notes = 0, 0, []
+
+    def cmp(tag, got, want):
+        nonlocal bad
+        for k, w in want.items():
+            g = got[k]
+            same = g.shape == w.shape and (np.array_equal(g.view(np.int32), w.view(np.int32)) if g.dtype == np.float32 else np.array_equal(g, w))
+            if not same:
+                bad += 1
+                notes.append(f"{tag}:{k}")
+
+    for i, seed in enumerate(pairs_seeds):
+        gp = os.path.join(golden_dir, f"ref_C2_seed{seed}.npz")
+        if cfg.name.startswith("C2") and os.path.exists(gp):
+            g = np.load(gp)
+            cmp(f"golden seed{seed}", get_pair(i), {k: g[k] for k in ("kps_l", "desc_l", "kps_r", "desc_r", "u_right", "depth")})
+            checked += 1
+    for i, seed in list(enumerate(pairs_seeds))[:n_oracle]:
+        L, R = synth.stereo_pair(cfg.height, cfg.width, seed)
+        ol, orr = orc.Oracle(**cfg.extractor_kwargs()), orc.Oracle(**cfg.extractor_kwargs())
+        kl, dl = ol.extract(L)
+        kr, dr = orr.extract(R)
+        ur, dp, _, _ = orc.stereo_match(ol, orr, kl, dl, kr, dr, cfg.mb, cfg.mbf)
+        cmp(f"oracle seed{seed}", get_pair(i), dict(kps_l=kl, desc_l=dl, kps_r=kr, desc_r=dr, u_right=ur, depth=dp))
+        checked += 1
+    return checked, bad, notes
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -290,37 +372,29 @@ def run_reference_arm(args, cfg):
     if rank != 0:
         return
     from jetson_slam_b200 import synth
-    cores = os.cpu_count() or 1
     imgs = [synth.stereo_pair(cfg.height, cfg.width, s) for s in range(4)]
-    # all the host threads the port can USE: with SMT and shared caches the fastest count is often below os.cpu_count(), so the
-    # warm-up tries cores, cores/2 and cores/4 threads on a small sample and the timed steps run the best of them
-    tried = {}
-    if args.cpu_threads:
-        threads = max(1, min(cores, args.cpu_threads))
-    else:
-        for t in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-            cpu_pairs_per_s(cfg, imgs, t, max(1, t // 4))                  # spin the threads up
-            tried[t] = cpu_pairs_per_s(cfg, imgs, t, 2 * t)[0]
-        threads = max(tried, key=tried.get)
-    per_step = 4 * threads  # bounded sample: four pairs per host thread per step (~0.3 s of CPU work per pair)
-    for _ in range(max(0, args.warmup - 1)):
+    threads, tried = best_cpu_threads(cfg, imgs, args.cpu_threads)
+    # bounded sample: a step is at most four pairs per host thread, and the K steps together about 30 s of wall clock
+    rate = max(tried.values()) if tried else cpu_pairs_per_s(cfg, imgs, threads, 2 * threads)[0]
+    per_step = max(1, min(4 * threads, int(rate * 30.0 / max(1, args.steps))))
+    for _ in range(max(0, min(args.warmup, 3) - 1)):
         cpu_pairs_per_s(cfg, imgs, threads, max(1, per_step // 4))
+    steps = args.steps
     t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         v, dt = cpu_pairs_per_s(cfg, imgs, threads, per_step)
         t_total += dt
         n_total += per_step
     value = n_total / t_total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": cfg.name, "pairs_per_step": per_step, "height": cfg.height, "width": cfg.width,
-                   "n_levels": cfg.n_levels, "tile": cfg.tile_h,
-                   "note": "the reference has no CPU extractor/matcher (SURVEY F2/F3); this arm is the CPU restatement "
-                           "(oracle port) of its CUDA path, one pair per host thread"},
+        "config": workload_config(cfg, args.pairs),
+        "note": "the reference has no CPU extractor/matcher (SURVEY F2/F3); this arm is the CPU restatement (oracle port) of its CUDA "
+                "path, one pair per host thread, on a bounded sample of the workload",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_total} C2 stereo pairs over {args.steps} steps, {threads} threads",
+                         "sample": f"{n_total} {cfg.name.split()[0]} stereo pairs over {steps} timed passes, {threads} threads",
                          "threads_tried": {str(k): v for k, v in tried.items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -345,6 +419,7 @@ def run_ours(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    numa = pin_to_gpu_numa(local)           # before any pinned allocation
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -363,12 +438,14 @@ def run_ours(args, cfg):
             os.close(saved)
 
     B = args.pairs
-    # distinct synthetic pairs (rank-dependent seeds), cycled over the slots
+    # distinct synthetic pairs cycled over the slots.  Rank 0 starts with seeds 0 and 1: the committed goldens of the reference's
+    # own kernels exist for them (tests/golden/ref_C2_seed{0,1}.npz), so the timed batch itself is checked against the reference.
     n_distinct = min(B, args.distinct)
-    pairs = [synth.stereo_pair(cfg.height, cfg.width, 1000 * rank + s) for s in range(n_distinct)]
+    seeds = [s if (rank == 0 and s < 2) else 1000 * rank + s for s in range(n_distinct)]
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, sd) for sd in seeds]
     # colour only: the reference's own src/cuda on this GPU, timed before this process owns any device memory of ours
     # (it allocates and frees per frame, which gets slower the more the process has mapped)
-    ref_cuda = ref_cuda_pairs_per_s(cfg, 1000 * rank) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
+    ref_cuda = ref_cuda_pairs_per_s(cfg, seeds[0]) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
     fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
     host = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
@@ -377,110 +454,125 @@ def run_ours(args, cfg):
     stream = torch.cuda.Stream()
     fe.set_images(hv, 0, stream)
     stream.synchronize()
-
-    gather = None
-    if args.gather and world > 1:
-        from jetson_slam_b200 import distributed as jd
-        local_slabs = jd.slab_tensors(fe, 0, 2 * B)
-
-        def gather():
-            # NCCL gather of the fixed-capacity result slabs to rank 0, enqueued behind the match kernels
-            with torch.cuda.stream(stream):
-                jd.gather_slabs(local_slabs, world * B, dst=0)
+    # the second handle: two batches in flight in the e2e loop, and the other half of the double buffer when results are gathered
+    fe_b = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
+    fe_b.set_images(hv, 0, stream)
+    stream.synchronize()
+    fes = (fe, fe_b)
 
     def step_device():
         fe.extract(0, 2 * B, stream)
         fe.stereo_match(cfg.mb, cfg.mbf, 0, B, stream=stream)
-        if gather:
-            gather()
 
     def step_e2e():
         # the public blocking end-to-end call: host images in, host result slabs out (chunked 3-stream pipeline inside)
         return fe.process_host_pairs(hv, cfg.mb, cfg.mbf, chunk_pairs=args.chunk)
 
-    # the same API split at its sync point, two handles: a batch is uploaded while the previous one computes
-    fe_b = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
-    fes = (fe, fe_b)
-
     # half-batch chunks: measured 41.5 k pairs/s vs 41.2 k (chunks of 32) and 30.9 k (one 160-pair chunk: a single long upload
     # does not overlap the other handle's kernels)
     ovl_chunk = int(os.environ.get("BENCH_OVL_CHUNK", max(1, B // 2)))
 
-    def steps_e2e_overlapped(k_steps):
+    def steps_e2e_overlapped(k_steps, stamps=None):
         fes[0].process_host_pairs_begin(hv, cfg.mb, cfg.mbf, chunk_pairs=ovl_chunk)
-        r = None
         for k in range(1, k_steps):
             fes[k % 2].process_host_pairs_begin(hv, cfg.mb, cfg.mbf, chunk_pairs=ovl_chunk)
-            r = fes[(k - 1) % 2].process_host_pairs_end()
-        return fes[(k_steps - 1) % 2].process_host_pairs_end()
+            fes[(k - 1) % 2].process_host_pairs_end()
+            if stamps is not None:
+                stamps.append(time.perf_counter())
+        r = fes[(k_steps - 1) % 2].process_host_pairs_end()
+        if stamps is not None:
+            stamps.append(time.perf_counter())
+        return r
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        stream.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
-            t = torch.tensor([ms], device="cuda")
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events on the launching stream around the region and after every step."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        ev[0].record(stream)
+        for k in range(steps):
+            fn(k)
+            ev[k + 1].record(stream)
+        stream.synchronize()
+        barrier()
+        per = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(steps)])
+        return max_over_ranks(ev[0].elapsed_time(ev[steps])), per
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = fe.launch_count()
-    ms = timed(step_device, args.steps)
+    ms, per_step = timed(lambda k: step_device(), args.steps)
     launches = fe.launch_count() - l0
     clocks = sampler.stop()
     value = world * B * args.steps / (ms / 1e3)
 
-    # e2e: host buffers in, host results out, every step
+    # ---- parity of the timed configuration (device-resident results of the distinct pairs), asserted in this run
+    parity = None
+    if rank == 0 and not args.no_parity:
+        stream.synchronize()
+
+        def dev_pair(i):
+            kl, dl = fe.get_keypoints(2 * i)
+            kr, dr = fe.get_keypoints(2 * i + 1)
+            ur, dp, _, _ = fe.get_stereo(i)
+            return dict(kps_l=kl, desc_l=dl, kps_r=kr, desc_r=dr, u_right=ur, depth=dp)
+        n_chk = min(n_distinct, 4)
+        checked, bad, notes = check_parity(cfg, seeds[:n_chk], dev_pair, os.path.join(ROOT, "tests", "golden"))
+        parity = {"checked_pairs": checked, "mismatches": bad, "against": "tests/golden/ref_C2_seed*.npz (the reference's own kernels) + CPU oracle",
+                  "path": "device-resident", "notes": notes[:8]}
+
+    # ---- e2e: host buffers in, host results out, every step
     for _ in range(2):
         step_e2e()
     # the e2e call is synchronous (it returns with the results on the host), so its time is wall-clock, max over ranks
+    e2e_steps = max(3, min(args.steps, 50))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         step_e2e()
     torch.cuda.synchronize()
-    wall_e2e = time.perf_counter() - t0
-    ms_e2e = wall_e2e * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e_serial = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
-    e2e_serial = world * B * args.steps / (ms_e2e / 1e3)
-    ms_e2e_serial = ms_e2e
+    e2e_serial = world * B * e2e_steps / (ms_e2e_serial / 1e3)
     # two batches in flight (begin/end over two handles): every step still uploads its 2*B images and downloads its result slabs
     steps_e2e_overlapped(3)
     barrier()
-    t0 = time.perf_counter()
-    steps_e2e_overlapped(args.steps)
+    stamps = [time.perf_counter()]
+    steps_e2e_overlapped(args.steps, stamps)
     torch.cuda.synchronize()
-    wall_e2e = time.perf_counter() - t0
-    ms_e2e = wall_e2e * 1e3
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    wall_e2e = time.perf_counter() - stamps[0]
+    ms_e2e = max_over_ranks(wall_e2e * 1e3)
+    e2e_per_step = np.diff(np.array(stamps)) * 1e3
     barrier()
     res = step_e2e()
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     n_mean = float(res["n"].mean())
     d2h = int(res["bytes"])
     matched = int((res["u_right"][0::2] >= 0).sum())
+    if parity is not None:     # the same pairs through the host-to-host call
+        cap = res["kps"].shape[2]
+
+        def e2e_pair(i):
+            nl, nr = int(res["n"][2 * i]), int(res["n"][2 * i + 1])
+            return dict(kps_l=np.array(res["kps"][2 * i, :, :nl]), desc_l=np.array(res["desc"][2 * i, :nl]), kps_r=np.array(res["kps"][2 * i + 1, :, :nr]),
+                        desc_r=np.array(res["desc"][2 * i + 1, :nr]), u_right=np.array(res["u_right"][2 * i, :nl]), depth=np.array(res["depth"][2 * i, :nl]))
+        c2, b2, n2 = check_parity(cfg, seeds[:min(n_distinct, 4)], e2e_pair, os.path.join(ROOT, "tests", "golden"), n_oracle=1)
+        parity["e2e_checked_pairs"], parity["e2e_mismatches"] = c2, b2
+        parity["notes"] = (parity["notes"] + n2)[:8]
     # what the PCIe link alone gives for this step's input (pinned host -> device, nothing else running): the floor under e2e
     dev_in = torch.empty_like(host, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -493,6 +585,83 @@ def run_ours(args, cfg):
     torch.cuda.synchronize()
     h2d_ms = ev0.elapsed_time(ev1) / 3
     del dev_in
+
+    # ---- N > 1: the same step with the results gathered on rank 0 (jsfe_gather_*), double-buffered over the two handles so that the
+    #      transfer of batch k overlaps the extraction of batch k+1
+    gather_info = None
+    if world > 1 and not args.no_gather:
+        from jetson_slam_b200 import distributed as jd
+        gs = [jd.Gatherer(f, B, root=0, transport=args.gather_transport) for f in fes]
+
+        def step_gather(k):
+            f, g = fes[k % 2], gs[k % 2]
+            if k >= 2:
+                g.end()                                  # batch k-2 of this handle has landed (and the root has released its buffer)
+            f.extract(0, 2 * B, stream)
+            f.stereo_match(cfg.mb, cfg.mbf, 0, B, stream=stream)
+            g.begin(0, B, stream)
+
+        def drain(k_steps):
+            for k in range(max(0, k_steps - 2), k_steps):
+                gs[k % 2].end()
+        for k in range(4):
+            step_gather(k)
+        drain(4)
+        barrier()
+        t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for k in range(args.steps):
+            step_gather(k)
+        ev1.record(stream)
+        drain(args.steps)
+        stream.synchronize()
+        wall = max_over_ranks((time.perf_counter() - t0) * 1e3)       # includes the last transfers (nothing left in flight)
+        barrier()
+        gval = world * B * args.steps / (wall / 1e3)
+        last = gs[(args.steps - 1) % 2].last
+        payload = None
+        if rank == 0:
+            regs = gs[(args.steps - 1) % 2].regions_to_host(last)
+            payload = [int(len(r)) for r in regs]
+            u = jd.unpack_region(regs[-1])               # the farthest rank's region decodes and carries that rank's batch
+            assert u["rank"] == world - 1 and u["n_pairs"] == B
+        gather_info = {"value": gval, "unit": UNIT, "efficiency_vs_no_gather": gval / value, "ms_per_step": wall / args.steps,
+                       "transport": gs[0].transport, "bytes_per_rank_per_step": payload,
+                       "how": "extract + match + jsfe_gather_begin per step, alternating two handles (batch k is packed and stored into rank 0's "
+                              "memory on the gather stream while batch k+1 is extracted); wall clock incl. the final transfers, max over ranks"}
+        for g in gs:
+            g.close()
+
+    # ---- BASELINE configs[4]: C5 1920x1080, one pair per GPU, gathered (latency of a batch request over all GPUs)
+    c5 = None
+    if world > 1 and not args.no_gather:
+        from jetson_slam_b200 import distributed as jd
+        from jetson_slam_b200.configs import CONFIGS
+        c5cfg = CONFIGS["C5"]
+        f5 = frontend.Frontend(**c5cfg.extractor_kwargs(), device=local, max_images=2)
+        p5 = synth.stereo_pair(c5cfg.height, c5cfg.width, 7000 + rank)
+        f5.set_images(np.stack(p5), 0, stream)
+        g5 = jd.Gatherer(f5, 1, root=0, transport=args.gather_transport)
+
+        def c5_batch():
+            f5.extract(0, 2, stream)
+            f5.stereo_match(c5cfg.mb, c5cfg.mbf, 0, 1, stream=stream)
+            g5.begin(0, 1, stream)
+            g5.end()
+        for _ in range(5):
+            c5_batch()
+        barrier()
+        t0 = time.perf_counter()
+        n5 = 50
+        for _ in range(n5):
+            c5_batch()
+        wall5 = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        c5 = {"workload": c5cfg.name, "pairs_per_batch": world, "ms_per_batch": wall5 / n5, "value": world * n5 / (wall5 / 1e3), "unit": UNIT,
+              "transport": g5.transport, "how": "one pair per GPU (device-resident images), extract + match + gather to rank 0, each batch waited for"}
+        g5.close()
+        f5.close()
 
     # single-pair latency (the reference's real-time use: one frame at a time), host images in -> host results out
     lat = None
@@ -509,11 +678,12 @@ def run_ours(args, cfg):
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e3
         lat = {"pairs_in_flight": 1, "median_ms": float(np.median(ts)), "p95_ms": float(np.percentile(ts, 95)),
-               "how": "jsfe_process_host_pairs(1 pair): pinned H2D + one CUDA-graph launch (re-pitch, 10 kernels, result copies) + sync, wall clock, 200 iterations"}
+               "how": "jsfe_process_host_pairs(1 pair): pinned H2D + one CUDA-graph launch (re-pitch, kernels, result copies) + sync, wall clock, 200 iterations"}
 
     # per-kernel durations (CUDA events on the launching stream around every launch)
     fe.profile(True)
-    for _ in range(args.steps):
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
         step_device()
     stream.synchronize()
     prof = fe.profile_read()
@@ -575,33 +745,34 @@ def run_ours(args, cfg):
             sweep[str(nb)] = ent
         return sweep
 
-
     if rank == 0:
         if lat is not None and world == 1:
             lat["device_resident_ladder"] = device_ladder()
-        cores = os.cpu_count() or 1
-        threads = max(1, min(cores, args.cpu_threads or 32))
-        sample_pairs = 6 * threads   # ~15 s of CPU work
-        cpu_v, cpu_dt = cpu_pairs_per_s(cfg, pairs[: min(4, len(pairs))], threads, sample_pairs)
+        cpu_threads, cpu_tried = best_cpu_threads(cfg, pairs[: min(4, len(pairs))], args.cpu_threads)
+        sample_pairs = 6 * cpu_threads   # ~15 s of CPU work
+        cpu_v, cpu_dt = cpu_pairs_per_s(cfg, pairs[: min(4, len(pairs))], cpu_threads, sample_pairs)
+        config = workload_config(cfg, B)
+        config["parallelism"] = f"pairs sharded one-batch-per-GPU x{world}, no data-path collective in `value`" + ("; `gather` adds the exchange step" if gather_info else "")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": cfg.name, "pairs_per_step_per_gpu": B, "height": cfg.height, "width": cfg.width,
-                       "n_levels": cfg.n_levels, "tile": cfg.tile_h, "max_keypoints_per_eye": fe.max_kp,
-                       "mean_keypoints_per_eye": n_mean, "stereo_matches_per_step": matched,
-                       "distinct_pairs": n_distinct, "l2": "inputs>L2 (%.0f MB of level-0 images per step)" % (2 * B * cfg.height * cfg.width / 1e6),
-                       "parallelism": f"pairs sharded one-batch-per-GPU x{world}, no data-path collective" +
-                                      (", NCCL gather of result slabs to rank 0 every step" if gather else "")},
+            "config": config,
+            "workload_stats": {"max_keypoints_per_eye": fe.max_kp, "mean_keypoints_per_eye": n_mean, "stereo_matches_per_step": matched,
+                               "distinct_pairs": n_distinct, "numa": numa},
+            "step_ms": {"median": float(np.median(per_step)), "p95": float(np.percentile(per_step, 95)), "min": float(per_step.min()),
+                        "max": float(per_step.max()), "n": int(len(per_step)), "how": "CUDA events after every step on the launching stream (this rank)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * cfg.height * cfg.width),
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "wall_s": wall_e2e,
+                    "step_ms": {"median": float(np.median(e2e_per_step)), "p95": float(np.percentile(e2e_per_step, 95)), "n": int(len(e2e_per_step))},
                     "how": "jsfe_process_host_pairs_begin/_end, two handles alternating (a batch uploads while the previous one computes); "
                            "pinned host images in, pinned host result slabs out, wall clock over all steps",
-                    "blocking_call": {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e_serial / args.steps,
+                    "blocking_call": {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e_serial / e2e_steps,
                                       "how": "one jsfe_process_host_pairs call per step (chunked 3-stream pipeline inside), nothing else in flight"},
                     "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": 2 * B * cfg.height * cfg.width / h2d_ms / 1e6},
             "gpu_launches": int(launches),
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": per_kernel[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, B if dom.startswith("k_stereo") else 2 * B), "peak_source": peak_src,
                          "ms_per_launch": per_kernel[dom]["ms_per_launch"], "share_of_step": per_kernel[dom]["share"]},
@@ -609,9 +780,14 @@ def run_ours(args, cfg):
                                   "frac": bpp * value / world / 1e9 / peak},
             "kernels": per_kernel,
             "latency": lat,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample_pairs} C2 stereo pairs on {threads} threads ({cpu_dt:.1f} s wall)"},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": f"{sample_pairs} {cfg.name.split()[0]} stereo pairs on {cpu_threads} threads ({cpu_dt:.1f} s wall)",
+                             "threads_tried": {str(k): v for k, v in cpu_tried.items()}},
         }
+        if gather_info is not None:
+            line["gather"] = gather_info
+        if c5 is not None:
+            line["c5_batch_gather"] = c5
         if ref_cuda is not None:
             line["ref_cuda"] = ref_cuda
         if world == 1:
@@ -624,13 +800,15 @@ def run_ours(args, cfg):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and (parity["mismatches"] or parity.get("e2e_mismatches")):
+        raise SystemExit(f"bench.py: PARITY FAILED {parity}")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--pairs", type=int, default=160, help="stereo pairs per step per GPU")
@@ -638,7 +816,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=32, help="pairs per pipeline chunk of the end-to-end call")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-ref-cuda", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="N>1: also gather every rank's result slabs to rank 0 (NCCL) each step")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the gather measurements")
+    ap.add_argument("--gather-transport", default="p2p", choices=["p2p", "nccl"], help="peer-memory stores over NVLink (CUDA IPC) or NCCL send/recv")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against goldens and oracle")
     args = ap.parse_args()
     from jetson_slam_b200.configs import CONFIGS
     cfg = CONFIGS[args.workload]

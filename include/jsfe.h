@@ -13,8 +13,9 @@
  * Model: a handle owns `max_images` image SLOTS on one GPU.  A slot is one eye: its level-0 image,
  * its pyramid, its keypoints/descriptors.  Stereo pair p uses slot 2p (left) and 2p+1 (right).
  * The reference's "one ORB_GPU per eye" maps to a handle with max_images = 1 (compat/) and the
- * batched B200 path to one handle with max_images = 2 * pairs.  All device memory is allocated in
- * jsfe_create; nothing is allocated on the per-frame path.  A handle is single-threaded; distinct
+ * batched B200 path to one handle with max_images = 2 * pairs.  All device memory of the extraction /
+ * matching path is allocated in jsfe_create (the upload staging buffer and the three streams of
+ * jsfe_process_host_pairs are created at its first use); nothing is allocated per frame.  A handle is single-threaded; distinct
  * handles may be driven concurrently from distinct host threads (the reference does this for L/R,
  * src/Frame.cpp:107-110).  Work is enqueued on the caller's CUDA stream (cudaStream_t passed as
  * void*; NULL = the legacy default stream); only the jsfe_get_* / jsfe_download_* calls synchronise.
@@ -268,6 +269,40 @@ int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pi
                         int64_t dst_stride, void* stream);
 int jsfe_cvt_gray(const uint8_t* src, int h, int w, int64_t src_pitch, int channels, int rgb_order, uint8_t* dst, int64_t dst_pitch,
                   void* stream);
+
+/* ---- the results of a batch from every GPU on one rank ("NCCL gather of keypoint/descriptor buffers only when a
+ * batch is requested", BASELINE config C5).  The reference has no counterpart (one device, src/cuda/orb_gpu.cpp:24).
+ * One process per GPU; each rank owns a handle and a jsfe_gather bound to it.  jsfe_gather_begin packs the results of pairs
+ * [first_pair, first_pair + n_pairs) -- trimmed to their keypoint counts -- into ONE region and moves it to the root on the gather's
+ * own stream, ordered after `compute_stream`; `compute_stream` is made to wait only for the local packing (tens of microseconds), so
+ * the transfer overlaps the next extraction.  Transport: if the non-root ranks mapped the root's landing buffers (CUDA IPC:
+ * jsfe_gather_ipc_export on the root, jsfe_gather_ipc_import everywhere else, jsfe_gather_set_peers_mapped(root, 1)), a copy kernel
+ * stores the trimmed region straight into the root's memory over NVLink and NCCL only carries two 4-byte all-reduces (double-buffer
+ * credit in front of the stores, completion behind them); otherwise the regions travel as one ncclSend/ncclRecv group, padded to
+ * the capacity bound.  The root's view of a batch stays valid until the root calls jsfe_gather_begin for the batch after the next.
+ * `nccl_comm` is an ncclComm_t the host owns (e.g. torch.distributed's); libnccl is resolved with dlopen.  world == 1 needs none.
+ *
+ * Region layout (all little endian; jsfe_gather_region_bytes() apart on the root, in rank order):
+ *    0  int32 magic 'JSG1', rank, n_pairs, capacity;  16  int64 payload_bytes;  24  int64 sequence;
+ *   32  int32 n_keypoints[2 * n_pairs]            (slot order L0, R0, L1, R1, ...), zero-padded to a multiple of 16 bytes
+ *   then one section per slot, each padded to 16 bytes:   int32 kps[6][n] | uint8 desc[n][32] | left slots only: float u_right[n], depth[n]
+ * The gathered bytes are a pure function of the inputs: the slot sections of a pair are identical whatever the number of ranks. */
+typedef struct jsfe_gather jsfe_gather;
+typedef struct jsfe_gathered {
+    const uint8_t* data;   /* root: DEVICE pointer to `world` regions; other ranks: NULL */
+    int64_t region_stride; /* bytes between the regions of consecutive ranks             */
+    int32_t world, root;
+    int32_t n_pairs;       /* pairs per rank in this gather                               */
+    int32_t transport;     /* 0: single rank, 1: peer-memory stores over NVLink, 2: NCCL send/recv */
+} jsfe_gathered;
+int64_t jsfe_gather_region_bytes(const jsfe_handle* h, int max_pairs);
+int jsfe_gather_create(jsfe_handle* h, void* nccl_comm, int rank, int world, int root, int max_pairs, jsfe_gather** out);
+int jsfe_gather_ipc_export(jsfe_gather* g, int buffer /* 0 | 1 */, uint8_t handle64[64]);
+int jsfe_gather_ipc_import(jsfe_gather* g, int buffer /* 0 | 1 */, const uint8_t handle64[64]);
+int jsfe_gather_set_peers_mapped(jsfe_gather* g, int all_mapped);
+int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute_stream);
+int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out); /* waits for the gather started by jsfe_gather_begin */
+int jsfe_gather_destroy(jsfe_gather* g);
 
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */
 int jsfe_debug_level_image(jsfe_handle* h, int slot, int level, uint8_t* host_dst /* h*w contiguous */);

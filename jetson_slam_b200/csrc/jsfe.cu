@@ -18,6 +18,9 @@
 
 #include "../../include/jsfe.h"
 #include "jsfe_kernels.cuh"
+#include "jsfe_gather.cuh"
+
+#include <dlfcn.h>
 
 namespace {
 
@@ -1193,6 +1196,218 @@ int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y,
     if (score) CU(cudaMemcpy(score, h->P.kp_s + o, cap * 4, cudaMemcpyDeviceToHost));
     if (level) CU(cudaMemcpy(level, h->P.kp_l + o, cap * 4, cudaMemcpyDeviceToHost));
     if (angle_rad) CU(cudaMemcpy(angle_rad, h->P.kp_angle + o, cap * 4, cudaMemcpyDeviceToHost));
+    return JSFE_OK;
+}
+
+
+// ================================================================================================= SURVEY.md 8(e): gather
+// NCCL is resolved at run time (dlopen): libjsfe.so has no link-time dependency on it, and inside a process that already loaded
+// an NCCL (torch's bundled one) the same library -- hence the same ncclComm_t -- is found by its soname.
+typedef struct ncclComm* jsfe_nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, jsfe_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, jsfe_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, jsfe_nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return JSFE_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(JSFE_ERR_INVALID, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+    NcclApi a;
+    a.lib = lib;
+    *(void**)&a.AllReduce = dlsym(lib, "ncclAllReduce");
+    *(void**)&a.Send = dlsym(lib, "ncclSend");
+    *(void**)&a.Recv = dlsym(lib, "ncclRecv");
+    *(void**)&a.GroupStart = dlsym(lib, "ncclGroupStart");
+    *(void**)&a.GroupEnd = dlsym(lib, "ncclGroupEnd");
+    *(void**)&a.GetErrorString = dlsym(lib, "ncclGetErrorString");
+    if (!a.AllReduce || !a.Send || !a.Recv || !a.GroupStart || !a.GroupEnd || !a.GetErrorString)
+        return fail(JSFE_ERR_INVALID, "libnccl lacks an expected symbol");
+    g_nccl = a;
+    return JSFE_OK;
+}
+#define NC(call)                                                                                                  \
+    do {                                                                                                          \
+        int r__ = (call);                                                                                         \
+        if (r__ != 0) return fail(JSFE_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r__));              \
+    } while (0)
+
+struct jsfe_gather {
+    jsfe_handle* h = nullptr;
+    jsfe_nccl_comm_t comm = nullptr;
+    int rank = 0, world = 1, root = 0, max_pairs = 0;
+    size_t region_bytes = 0;            // stride between rank regions (capacity bound, 256-aligned)
+    uint8_t* stage = nullptr;           // this rank's packed region in local HBM (the root packs straight into its landing buffer)
+    uint8_t* landing[2] = {nullptr, nullptr};   // root: [world][region_bytes] x 2 (double buffer)
+    uint8_t* peer[2] = {nullptr, nullptr};      // non-root: the root's landing buffers mapped through CUDA IPC (nullptr: NCCL transport)
+    int32_t* token = nullptr;           // 2 ints: all-reduce send / receive
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_packed = nullptr, ev_done[2] = {nullptr, nullptr};
+    long long seq = 0;
+    int last_pairs = 0, in_flight = 0;
+    bool peer_all_mapped = false;       // root: every other rank writes its region through a peer mapping (no NCCL receive posted)
+};
+
+int64_t jsfe_gather_region_bytes(const jsfe_handle* h, int max_pairs) {
+    if (!h || max_pairs < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    const size_t cap = (size_t)h->P.cap;
+    return (int64_t)align_up(jsfe::gather_header_bytes(max_pairs) + (size_t)max_pairs * (jsfe::gather_slot_bytes((int)cap, 1) + jsfe::gather_slot_bytes((int)cap, 0)), 256);
+}
+
+int jsfe_gather_destroy(jsfe_gather* g) {
+    if (!g) return JSFE_OK;
+    cudaSetDevice(g->h->device);
+    if (g->st) cudaStreamSynchronize(g->st);
+    for (int b = 0; b < 2; ++b) {
+        if (g->peer[b]) cudaIpcCloseMemHandle(g->peer[b]);
+        if (g->landing[b]) cudaFree(g->landing[b]);
+        if (g->ev_done[b]) cudaEventDestroy(g->ev_done[b]);
+    }
+    if (g->stage) cudaFree(g->stage);
+    if (g->token) cudaFree(g->token);
+    if (g->ev_ready) cudaEventDestroy(g->ev_ready);
+    if (g->ev_packed) cudaEventDestroy(g->ev_packed);
+    if (g->st) cudaStreamDestroy(g->st);
+    delete g;
+    return JSFE_OK;
+}
+
+int jsfe_gather_create(jsfe_handle* h, void* nccl_comm, int rank, int world, int root, int max_pairs, jsfe_gather** out) {
+    if (!h || !out || world < 1 || rank < 0 || rank >= world || root < 0 || root >= world || max_pairs < 1 || 2 * max_pairs > h->max_images)
+        return fail(JSFE_ERR_INVALID, "bad gather geometry");
+    *out = nullptr;
+    if (world > 1) {
+        if (!nccl_comm) return fail(JSFE_ERR_INVALID, "a communicator (ncclComm_t) is required for world > 1");
+        int rc = nccl_load();
+        if (rc) return rc;
+    }
+    CU(cudaSetDevice(h->device));
+    jsfe_gather* g = new (std::nothrow) jsfe_gather;
+    if (!g) return fail(JSFE_ERR_INVALID, "out of host memory");
+    g->h = h; g->comm = (jsfe_nccl_comm_t)nccl_comm; g->rank = rank; g->world = world; g->root = root; g->max_pairs = max_pairs;
+    g->region_bytes = (size_t)jsfe_gather_region_bytes(h, max_pairs);
+    cudaError_t e = cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_packed, cudaEventDisableTiming);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&g->ev_done[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->token, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(g->token, 0, 2 * sizeof(int32_t));
+    if (e == cudaSuccess && rank != root) e = cudaMalloc((void**)&g->stage, g->region_bytes);
+    for (int b = 0; b < 2 && e == cudaSuccess && rank == root; ++b) {
+        e = cudaMalloc((void**)&g->landing[b], g->region_bytes * (size_t)world);
+        if (e == cudaSuccess) e = cudaMemset(g->landing[b], 0, g->region_bytes * (size_t)world);
+    }
+    if (e != cudaSuccess) {
+        jsfe_gather_destroy(g);
+        return fail(JSFE_ERR_CUDA, "gather set-up failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaDeviceSynchronize());
+    *out = g;
+    return JSFE_OK;
+}
+
+int jsfe_gather_ipc_export(jsfe_gather* g, int buffer, uint8_t handle64[64]) {
+    if (!g || !handle64 || buffer < 0 || buffer > 1 || g->rank != g->root) return fail(JSFE_ERR_INVALID, "only the root exports its landing buffers");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CU(cudaSetDevice(g->h->device));
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, g->landing[buffer]));
+    memcpy(handle64, &hnd, 64);
+    return JSFE_OK;
+}
+
+int jsfe_gather_ipc_import(jsfe_gather* g, int buffer, const uint8_t handle64[64]) {
+    if (!g || !handle64 || buffer < 0 || buffer > 1 || g->rank == g->root) return fail(JSFE_ERR_INVALID, "only non-root ranks import");
+    CU(cudaSetDevice(g->h->device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    g->peer[buffer] = (uint8_t*)ptr;
+    return JSFE_OK;
+}
+
+int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute_stream) {
+    if (!g || n_pairs < 1 || n_pairs > g->max_pairs) return fail(JSFE_ERR_INVALID, "bad pair range for this gather");
+    jsfe_handle* h = g->h;
+    int rc = check_slots(h, 2 * first_pair, 2 * n_pairs);
+    if (rc) return rc;
+    if (g->in_flight) return fail(JSFE_ERR_INVALID, "a gather is already in flight (call jsfe_gather_end)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t cs = (cudaStream_t)compute_stream;
+    const int b = (int)(g->seq & 1);
+    const bool is_root = g->rank == g->root;
+    const bool p2p = !is_root && g->peer[0] && g->peer[1];
+    CU(cudaEventRecord(g->ev_ready, cs));
+    CU(cudaStreamWaitEvent(g->st, g->ev_ready, 0));
+    // pack in local HBM (the root: straight into its own region of the landing buffer)
+    uint8_t* region = is_root ? g->landing[b] + (size_t)g->rank * g->region_bytes : g->stage;
+    jsfe::k_gather_pack<<<2 * n_pairs, 256, 0, g->st>>>(h->P, first_pair, n_pairs, g->rank, g->seq, region);
+    if ((rc = post_launch(h, "k_gather_pack"))) return rc;
+    CU(cudaEventRecord(g->ev_packed, g->st));
+    CU(cudaStreamWaitEvent(cs, g->ev_packed, 0));      // the results may be overwritten once they are packed
+    if (g->world > 1) {
+        const size_t bound = jsfe::gather_header_bytes(n_pairs) + (size_t)n_pairs * (jsfe::gather_slot_bytes(h->P.cap, 1) + jsfe::gather_slot_bytes(h->P.cap, 0));
+        // every rank uses the same transport: the peer mappings are made on all non-root ranks or on none (the root is told with
+        // jsfe_gather_set_peers_mapped)
+        const bool use_p2p = is_root ? g->peer_all_mapped : p2p;
+        if (use_p2p) {
+            // credit: the root joins this all-reduce in ITS jsfe_gather_begin of this batch, i.e. after its consumer released the landing
+            // buffer of two batches ago -- no rank stores into that buffer earlier
+            NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
+            if (!is_root) {
+                const int blocks = (int)std::min<size_t>((bound / 16 + 255) / 256, 148 * 8);
+                jsfe::k_gather_put<<<blocks, 256, 0, g->st>>>(g->stage, g->peer[b] + (size_t)g->rank * g->region_bytes, n_pairs);
+                if ((rc = post_launch(h, "k_gather_put"))) return rc;
+            }
+            // completion: behind this all-reduce every rank's stores of this batch have been performed (kernel completion makes them
+            // visible system-wide), so the root may read all regions
+            NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
+        } else {
+            // NCCL transport: one send/recv group, padded to the capacity bound (the trimmed size is known on the device only)
+            NC(g_nccl.GroupStart());
+            if (is_root) {
+                for (int r = 0; r < g->world; ++r)
+                    if (r != g->root) NC(g_nccl.Recv(g->landing[b] + (size_t)r * g->region_bytes, bound, 1 /* ncclUint8 */, r, g->comm, g->st));
+            } else {
+                NC(g_nccl.Send(g->stage, bound, 1 /* ncclUint8 */, g->root, g->comm, g->st));
+            }
+            NC(g_nccl.GroupEnd());
+        }
+    }
+    CU(cudaEventRecord(g->ev_done[b], g->st));
+    g->last_pairs = n_pairs;
+    g->in_flight = 1;
+    ++g->seq;
+    return JSFE_OK;
+}
+
+int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out) {
+    if (!g || !out) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (!g->in_flight) return fail(JSFE_ERR_INVALID, "no gather in flight");
+    CU(cudaSetDevice(g->h->device));
+    const int b = (int)((g->seq - 1) & 1);
+    g->in_flight = 0;
+    CU(cudaEventSynchronize(g->ev_done[b]));
+    const bool is_root = g->rank == g->root;
+    out->data = is_root ? g->landing[b] : nullptr;
+    out->region_stride = (int64_t)g->region_bytes;
+    out->world = g->world;
+    out->root = g->root;
+    out->n_pairs = g->last_pairs;
+    out->transport = g->world == 1 ? 0 : (is_root ? (g->peer_all_mapped ? 1 : 2) : ((g->peer[0] && g->peer[1]) ? 1 : 2));
+    return JSFE_OK;
+}
+
+int jsfe_gather_set_peers_mapped(jsfe_gather* g, int all_mapped) {
+    if (!g) return fail(JSFE_ERR_INVALID, "null gather");
+    g->peer_all_mapped = all_mapped != 0;
     return JSFE_OK;
 }
 

@@ -51,6 +51,11 @@ class HostResults(C.Structure):
                 ("bytes", C.c_int64)]
 
 
+class Gathered(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("region_stride", C.c_int64), ("world", C.c_int32), ("root", C.c_int32),
+                ("n_pairs", C.c_int32), ("transport", C.c_int32)]
+
+
 _lib = None
 
 
@@ -100,6 +105,15 @@ def lib():
         L.jsfe_profile_read.argtypes = [vp, vp, vp, C.c_int]
         L.jsfe_launch_count.restype = C.c_int64
         L.jsfe_launch_count.argtypes = [vp]
+        L.jsfe_gather_region_bytes.restype = C.c_int64
+        L.jsfe_gather_region_bytes.argtypes = [vp, C.c_int]
+        L.jsfe_gather_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.jsfe_gather_ipc_export.argtypes = [vp, C.c_int, vp]
+        L.jsfe_gather_ipc_import.argtypes = [vp, C.c_int, vp]
+        L.jsfe_gather_set_peers_mapped.argtypes = [vp, C.c_int]
+        L.jsfe_gather_begin.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.jsfe_gather_end.argtypes = [vp, C.POINTER(Gathered)]
+        L.jsfe_gather_destroy.argtypes = [vp]
         _lib = L
     return _lib
 

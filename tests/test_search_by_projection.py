@@ -1,15 +1,22 @@
 """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) fused on the device.
 
-CPU part : the C oracle (oracle/jsfe_oracle.c: orc_search_by_projection) against an independent, literal pure-Python
-           transliteration of the reference's host loops (src/ORBmatcher.cpp:1647-1963, src/Frame.cpp:464-479,569-639,
-           696-706) in float32 arithmetic, plus the sequential-semantics corner cases.
-GPU part : the CUDA path through the C ABI (jsfe_build_frame_grid + jsfe_search_by_projection) bit-exact against the oracle.
-The host code being restated cannot be built here (Frame/MapPoint/OpenCV), so this row's parity is UNPINNED."""
+Pin      : tests/golden/ref_sbp_*.npz are outputs of the REFERENCE'S OWN host code -- src/ORBmatcher.cpp:1647-1963 and :2097-2138,
+           src/Frame.cpp:464-479, 569-639 and 696-706, cut out of the reference checkout by line range at build time and compiled
+           unmodified against minimal Frame / MapPoint / cv::Mat stand-ins (oracle/ref_build/sbp_slice/, `make -C oracle/ref_build
+           sbp`); its two device calls run the oracle's restatements of those kernels, which are pinned against the reference's
+           kernels on a B200 (tests/test_helpers.py).  tools/make_golden_sbp.py wrote the fixtures; tests/sbp_cases.py regenerates
+           the inputs from seeds.
+CPU part : the C oracle (oracle/jsfe_oracle.c: orc_search_by_projection) against those fixtures (and live against the reference
+           slice where oracle/_ref/libsbpref.so exists), against an independent pure-Python transliteration of the host loops in
+           float32 arithmetic, plus the sequential-semantics corner cases.
+GPU part : the CUDA path through the C ABI (jsfe_build_frame_grid + jsfe_search_by_projection) bit-exact against the oracle AND
+           against the reference fixtures."""
 import math
 
 import numpy as np
 import pytest
 
+import sbp_cases
 from jetson_slam_b200 import synth
 from oracle import oracle as orc
 
@@ -137,6 +144,49 @@ def assert_same(a, b):
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
 
 
+# --------------------------------------------------------------------------------- reference fixtures (the parity pin of row f1)
+def _fixture(name):
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_sbp_{name}.npz"))
+    c = sbp_cases.build(name)
+    assert int(g["input_checksum"]) == sbp_cases.checksum(c), "the seeded inputs changed: regenerate with tools/make_golden_sbp.py"
+    assert int(g["level_mode"]) == c["expect_mode"], "bForward / bBackward of the reference's pose test"
+    return c, int(g["nmatches"]), g["cur_match"]
+
+
+def _api_kwargs(c):
+    return dict(th=c["th"], level_mode=c["expect_mode"], check_orientation=c["check_orientation"])
+
+
+@pytest.mark.parametrize("name", list(sbp_cases.CASES))
+def test_oracle_equals_the_reference_host_code(name):
+    c, want_n, want_cm = _fixture(name)
+    r = run_oracle(c["kept_last"], c["frame_cur"], c["R"], c["t"], **_api_kwargs(c))
+    assert r["nmatches"] == want_n and want_n > 100
+    assert np.array_equal(sbp_cases.oracle_api_result_in_frame_indices(r, c, len(want_cm)), want_cm)
+
+
+def test_reference_slice_live_when_built():
+    """Where the reference slice is present (this container: /root/reference mounted at build time), run it instead of reading its
+    stored outputs: a new seed, so that the fixtures are not the only inputs the restatement has ever seen."""
+    from oracle import ref_sbp
+    if not ref_sbp.available():
+        pytest.skip("oracle/_ref/libsbpref.so not built (needs the reference checkout)")
+    for seed, mode in ((91, 0), (92, 1), (93, 2)):
+        sbp_cases.CASES["_live"] = (dict(n_cur=1100, n_last=800, seed=seed), 7.0 if mode != 1 else 15.0, mode, False, True, 0.15, 0.05)
+        try:
+            c = sbp_cases.build("_live")
+        finally:
+            del sbp_cases.CASES["_live"]
+        ref = ref_sbp.search_by_projection(c["frame_last"], c["frame_cur"], c["pose_last"], c["pose_cur"], **c["camera"], th=c["th"],
+                                           scale_factors=sbp_cases.SF, mono=c["mono"], check_orientation=c["check_orientation"])
+        assert ref["level_mode"] == mode
+        r = run_oracle(c["kept_last"], c["frame_cur"], c["R"], c["t"], **_api_kwargs(c))
+        assert r["nmatches"] == ref["nmatches"] > 100
+        assert np.array_equal(sbp_cases.oracle_api_result_in_frame_indices(r, c, len(ref["cur_match"])), ref["cur_match"])
+
+
 # ---------------------------------------------------------------------------------------------------------- CPU tests
 def test_grid_matches_the_host_loops():
     _, cur, _, _ = make_scene(n_cur=2000, seed=3)
@@ -223,6 +273,15 @@ def test_cuda_matches_oracle(level_mode, th, check):
     assert np.array_equal(got["grid"][0], start) and np.array_equal(got["grid"][1][:len(items)], items)
     assert_same(got, want)
     assert want["nmatches"] > 500
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(sbp_cases.CASES))
+def test_cuda_equals_the_reference_host_code(name):
+    c, want_n, want_cm = _fixture(name)
+    got = run_cuda(c["kept_last"], c["frame_cur"], c["R"], c["t"], **_api_kwargs(c))
+    assert got["nmatches"] == want_n
+    assert np.array_equal(sbp_cases.oracle_api_result_in_frame_indices(got, c, len(want_cm)), want_cm)
 
 
 @pytest.mark.gpu
