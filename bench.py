@@ -58,7 +58,6 @@ def kernel_algorithmic_bytes(levels_hw, cap, n_mean):
         "k_stereo_match": n_mean * (64 + 462 + 8),     # per PAIR: 2 descriptors, two 11x21 strips, uRight+depth
         "k_stereo_outlier": n_mean * 4,                # per PAIR
         "k_nms_ms": 12 * cap,
-        "k_blur_fix": 0.0012 * (p0 + prest) * 50,       # ~0.12 % of pixels re-read their 7x7 window
     }
 
 
@@ -282,6 +281,33 @@ def ref_cuda_pairs_per_s(cfg, seed=0, iters=40):
             return {"unavailable": (r.stderr or r.stdout)[-200:]}
         return json.loads(last[-1])
     except Exception as e:  # the reference library is optional colour, never the measured product
+        return {"unavailable": repr(e)[:200]}
+
+
+def compat_api_fps(cfg, pair, frames=300):
+    """The reference-API path a Jetson-SLAM user calls, through compat/: tests/cpp/frame_hotpath replays Frame::Frame's hot path (two
+    extractor threads on two ORBExtractor shims, 4 D2H, SoA unpack, ORB_compute_stereo_match; src/Frame.cpp:103-122,124-196,780-803)
+    `frames` times.  Compare with ref_cuda.detail.two_threads: the reference's own kernels under the same call pattern."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "tests", "cpp", "frame_hotpath")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/cpp/frame_hotpath not built"}
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            lp, rp, op = (os.path.join(d, n) for n in ("l.raw", "r.raw", "o.bin"))
+            pair[0].tofile(lp)
+            pair[1].tofile(rp)
+            cmd = [exe, str(cfg.height), str(cfg.width), str(cfg.n_levels), str(cfg.scale_factor), str(cfg.fast_n_min), str(cfg.fast_n_max),
+                   str(cfg.th_fast_min), str(cfg.th_fast_max), str(cfg.tile_h), str(cfg.tile_w), lp, rp, repr(cfg.mb), repr(cfg.mbf), op,
+                   "--time", str(frames)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        fps = [float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("fps ")]
+        if r.returncode != 0 or not fps:
+            return {"unavailable": (r.stderr or r.stdout)[-200:]}
+        return {"value": fps[0], "unit": UNIT, "frames": frames,
+                "how": "compat/ shims driven like Frame::Frame (2 extractor threads, 4 D2H, unpack, stereo match), one pair at a time, wall clock"}
+    except Exception as e:
         return {"unavailable": repr(e)[:200]}
 
 
@@ -791,6 +817,9 @@ def run_ours(args, cfg):
         if ref_cuda is not None:
             line["ref_cuda"] = ref_cuda
         if world == 1:
+            ours_api = compat_api_fps(cfg, pairs[0])
+            line["compat_api"] = {"ours": ours_api, "ref_cuda": (ref_cuda or {}).get("detail", {}).get("two_threads"),
+                                  "note": "pairs/s of the reference's own per-frame interface (Jetson_SLAM::ORBExtractor x2 + ORB_GPU::ORB_compute_stereo_match)"}
             line["opencv_cpu_orb"] = opencv_orb_pairs_per_s(cfg, pairs[0])
             try:
                 line["adjacent"] = {"search_by_projection": sbp_microbench(), "remap_bilinear": remap_microbench()}

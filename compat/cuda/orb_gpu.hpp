@@ -33,7 +33,7 @@ class ORB_GPU {
         if (rc != 0) { fprintf(stderr, "jsfe: %s failed (%d): %s\n", what, rc, jsfe_last_error()); abort(); }
     }
     // right-eye lookup for ORB_compute_stereo_match: level-0 device pointer -> handle
-    static std::map<const void*, jsfe_handle*>& registry() { static std::map<const void*, jsfe_handle*> r; return r; }
+    static std::map<const void*, ORB_GPU*>& registry() { static std::map<const void*, ORB_GPU*> r; return r; }
     static std::mutex& registry_mutex() { static std::mutex m; return m; }
 
 public:
@@ -47,10 +47,16 @@ public:
         c.apply_nms_ms = apply_nms_ms; c.nms_ms_mode_gpu = nms_ms_mode_gpu;
         c.mask = nullptr; c.mask_pitch = 0; c.device_id = device_id; c.max_images = 1;
         cv::Mat mask = cv::imread(str_mask);            // the reference loads its mask from a file (orb_gpu.cpp:64-91)
-        cv::Mat gray;
+        cv::Mat gray, fitted;
         if (!mask.empty()) {
             cv::cvtColor(mask, gray, 6 /* CV_BGR2GRAY */);
-            c.mask = gray.data; c.mask_pitch = gray.cols;
+            // the reference accepts a mask of ANY size and cv::resize's it to every level (orb_gpu.cpp:78-90); jsfe_create wants the
+            // level-0 geometry, so bring it there first with the same nearest-neighbour rule (resizing twice with INTER_NEAREST from
+            // the original grid equals resizing once only when the mask already has the frame size -- the common case -- and is the
+            // closest the C ABI's height x width mask can get otherwise)
+            if (gray.rows != im_height || gray.cols != im_width) cv::resize(gray, fitted, cv::Size(im_width, im_height), 0, 0, 0 /* INTER_NEAREST */);
+            else fitted = gray;
+            c.mask = fitted.data; c.mask_pitch = fitted.cols;
         }
         check(jsfe_create(&c, &h_), "jsfe_create");
         n_levels_ = n_levels;
@@ -67,7 +73,7 @@ public:
         }
         n_keypoints_.assign(n_levels, 0);
         std::lock_guard<std::mutex> g(registry_mutex());
-        registry()[image_[0].gpu_data_] = h_;
+        registry()[image_[0].gpu_data_] = this;
     }
     ~ORB_GPU() {
         {
@@ -81,15 +87,18 @@ public:
 
     // src/cuda/orb_gpu.cpp:489-841: on return the DEVICE buffers of the outputs are complete; host copies are the
     // caller's job (Frame.cpp:119-122).  Output layout: 6 planes x N (x|y|score|angle|octave|size), descriptors 32 x N.
+    // One stream synchronisation per call: the output buffers are grown to the capacity once, the pack kernel reads N on the device.
     void extract(const cv::Mat& image, SyncedMem<int>& out_keypoints, SyncedMem<unsigned char>& out_keypoints_desc) {
         check(jsfe_set_images(h_, 0, 1, image.data, image.cols, (int64_t)image.cols * image.rows, 0, nullptr), "jsfe_set_images");
         check(jsfe_extract(h_, 0, 1, nullptr), "jsfe_extract");
+        if (out_keypoints.capacity_ < 6 * max_kp_count_) out_keypoints.resize(6 * max_kp_count_);
+        if (out_keypoints_desc.capacity_ < 32 * max_kp_count_) out_keypoints_desc.resize(32 * max_kp_count_);
         int32_t n = 0;
-        check(jsfe_pack_keypoints(h_, 0, nullptr, nullptr, &n, nullptr), "jsfe_pack_keypoints");
-        out_keypoints.resize(6 * n);
+        check(jsfe_pack_keypoints_once(h_, 0, out_keypoints.gpu_data(), out_keypoints_desc.gpu_data(), &n, nullptr), "jsfe_pack_keypoints_once");
+        out_keypoints.resize(6 * n);            // shrinks count_ only (the reference's resize never gives memory back either)
         out_keypoints_desc.resize(32 * n);
-        check(jsfe_pack_keypoints(h_, 0, out_keypoints.gpu_data(), out_keypoints_desc.gpu_data(), &n, nullptr), "jsfe_pack_keypoints");
-        cudaStreamSynchronize(nullptr);
+        last_desc_dev_ = out_keypoints_desc.gpu_data();
+        last_n_ = n;
     }
 
     // src/cuda/orb_stereo_match.cu:105-580.  The keypoints/descriptors of both eyes are the ones the two extractors
@@ -97,16 +106,26 @@ public:
     void ORB_compute_stereo_match(int ORB_TH_HIGH, int ORB_TH_LOW, float mb, float mbf, std::vector<int>& /*octave_height*/,
                                   std::vector<int>& /*octave_width*/, std::vector<cv::KeyPoint>& mvKeys,
                                   std::vector<cv::KeyPoint>& mvKeysRight, std::vector<float>& mvuRight, std::vector<float>& mvDepth,
-                                  unsigned char* /*keypoint_descriptor_left*/, unsigned char* /*keypoint_descriptor_right*/,
+                                  unsigned char* keypoint_descriptor_left, unsigned char* keypoint_descriptor_right,
                                   std::vector<SyncedMem<unsigned char> >& /*images_left_smem*/,
                                   std::vector<SyncedMem<unsigned char> >& images_right_smem) {
-        jsfe_handle* hr = nullptr;
+        ORB_GPU* right = nullptr;
         {
             std::lock_guard<std::mutex> g(registry_mutex());
             auto it = registry().find(images_right_smem.empty() ? nullptr : images_right_smem[0].gpu_data_);
-            if (it != registry().end()) hr = it->second;
+            if (it != registry().end()) right = it->second;
         }
-        if (!hr) { fprintf(stderr, "jsfe: right pyramid does not belong to a live ORB_GPU\n"); abort(); }
+        if (!right) { fprintf(stderr, "jsfe: right pyramid does not belong to a live ORB_GPU\n"); abort(); }
+        jsfe_handle* hr = right->h_;
+        // The matcher works on the keypoints and descriptors the two extractors still hold on the device.  What the caller passes
+        // must be exactly those: the descriptor buffers of the last extract() of each eye, and as many keypoints as they hold
+        // (src/Frame.cpp:784-800 passes them untouched).  Anything else would silently be ignored, so it is refused.
+        if (keypoint_descriptor_left != last_desc_dev_ || keypoint_descriptor_right != right->last_desc_dev_ ||
+            (int)mvKeys.size() != last_n_ || (int)mvKeysRight.size() != right->last_n_) {
+            fprintf(stderr, "jsfe: ORB_compute_stereo_match was handed keypoints/descriptors other than the ones of the last extract() "
+                            "(left %zu vs %d, right %zu vs %d)\n", mvKeys.size(), last_n_, mvKeysRight.size(), right->last_n_);
+            abort();
+        }
         check(jsfe_stereo_match_cross(h_, 0, hr, 0, ORB_TH_HIGH, ORB_TH_LOW, mb, mbf, nullptr), "jsfe_stereo_match_cross");
         const size_t N = mvKeys.size();
         mvuRight.resize(N, -1.0f);
@@ -114,7 +133,7 @@ public:
         std::vector<float> ur(max_kp_count_), dp(max_kp_count_);
         int32_t n = 0;
         check(jsfe_get_stereo_slot(h_, 0, ur.data(), dp.data(), nullptr, nullptr, &n, nullptr), "jsfe_get_stereo_slot");
-        if ((size_t)n != N || mvKeysRight.empty()) { if ((size_t)n != N) { fprintf(stderr, "jsfe: %zu left keypoints passed, %d on the device\n", N, n); abort(); } }
+        if ((size_t)n != N) { fprintf(stderr, "jsfe: %zu left keypoints passed, %d on the device\n", N, n); abort(); }
         for (size_t i = 0; i < N; ++i) { mvuRight[i] = ur[i]; mvDepth[i] = dp[i]; }
     }
 
@@ -131,6 +150,8 @@ public:
 
 private:
     jsfe_handle* h_ = nullptr;
+    const unsigned char* last_desc_dev_ = nullptr;   // the caller's descriptor buffer filled by the last extract()
+    int last_n_ = -1;
 };
 
 }  // namespace orb_cuda

@@ -18,23 +18,31 @@ namespace orb_cuda {
 
 template <typename Dtype>
 class SyncedMem {
+    // The stream and the buffers are reference-counted SEPARATELY: copies of a SyncedMem share both, and a resize() of one copy
+    // replaces only its buffers -- the stream stays alive for every copy that still holds the handle (cu_stream_ is public).
+    struct Stream {
+        cudaStream_t s = nullptr;
+        Stream() { cudaStreamCreate(&s); }
+        ~Stream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+    };
     struct Block {
         Dtype* cpu = nullptr;
         Dtype* gpu = nullptr;
-        cudaStream_t stream = nullptr;
+        std::shared_ptr<Stream> stream;     // work on this stream may still use the buffers: drain it before they go
         ~Block() {
-            if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+            if (stream && stream->s) cudaStreamSynchronize(stream->s);
             if (cpu) cudaFreeHost(cpu);
             if (gpu) cudaFree(gpu);
         }
     };
+    std::shared_ptr<Stream> stream_;
     std::shared_ptr<Block> block_;
 
 public:
-    SyncedMem(void) : block_(std::make_shared<Block>()) {
+    SyncedMem(void) : stream_(std::make_shared<Stream>()), block_(std::make_shared<Block>()) {
         count_ = 0; capacity_ = 0; cpu_data_ = nullptr; gpu_data_ = nullptr; pitch_ = 0; cu_error_ = cudaSuccess;
-        cudaStreamCreate(&block_->stream);
-        cu_stream_ = block_->stream;
+        block_->stream = stream_;
+        cu_stream_ = stream_->s;
     }
     // non-owning device view (used for ORB_GPU::image_)
     static SyncedMem view(Dtype* dev, int count, size_t pitch) {
@@ -48,12 +56,12 @@ public:
         count_ = count;
         if (capacity_ < count_) {
             auto nb = std::make_shared<Block>();
-            nb->stream = block_->stream; block_->stream = nullptr;   // keep the stream, replace the buffers
+            nb->stream = stream_;                                     // same stream, new buffers (the old block drains it when it dies)
             cu_error_ = cudaMallocHost((void**)&nb->cpu, sizeof(Dtype) * count_);
             if (cu_error_ == cudaSuccess) cu_error_ = cudaMalloc((void**)&nb->gpu, sizeof(Dtype) * count_);
             capacity_ = count_;
             block_ = nb;
-            cpu_data_ = nb->cpu; gpu_data_ = nb->gpu; cu_stream_ = nb->stream;
+            cpu_data_ = nb->cpu; gpu_data_ = nb->gpu; cu_stream_ = stream_->s;
         }
     }
     void resize_pitched(size_t width, size_t height) {

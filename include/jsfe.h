@@ -141,6 +141,10 @@ int jsfe_level_image(const jsfe_handle* h, int slot, int level, const uint8_t** 
  * (this call synchronises `stream` to learn N). dst_kps needs 6*capacity ints, dst_desc 32*capacity. */
 int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out,
                         void* stream);
+/* The same packing with ONE synchronisation: the buffers must hold the capacity (6*jsfe_max_keypoints() ints, 32*jsfe_max_keypoints()
+ * bytes); the pack kernel reads N on the device, N is copied back behind it and `stream` is synchronised once.  On return the
+ * device buffers are complete and *n_out = N (planes with stride N, as the reference returns them). */
+int jsfe_pack_keypoints_once(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out, void* stream);
 /* Host copies (synchronise `stream`).  kps_host: 6*N ints with stride N (reference layout), desc_host 32*N;
  * either may be NULL.  Capacity of the host buffers must be jsfe_max_keypoints(). */
 int jsfe_get_keypoints(jsfe_handle* h, int slot, int32_t* kps_host, uint8_t* desc_host, int32_t* n_out, void* stream);
@@ -315,7 +319,7 @@ int jsfe_debug_level_keypoints(jsfe_handle* h, int slot, int32_t* x, int32_t* y,
  * stream.  jsfe_profile_read synchronises those events, returns the accumulated milliseconds and launch counts
  * per stage (JSFE_STAGE_*) since the last read, and resets the accumulators. */
 enum { JSFE_STAGE_PYRAMID = 0, JSFE_STAGE_FAST_CELLS = 1, JSFE_STAGE_COMPACT = 2, JSFE_STAGE_ORIENT_DESC = 3,
-       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_STAGE_BLUR = 7, JSFE_STAGE_BLUR_FIX = 8, JSFE_NUM_STAGES = 9 };
+       JSFE_STAGE_STEREO_MATCH = 4, JSFE_STAGE_STEREO_OUTLIER = 5, JSFE_STAGE_NMS_MS = 6, JSFE_STAGE_BLUR = 7, JSFE_NUM_STAGES = 8 };
 int jsfe_profile_enable(jsfe_handle* h, int on);
 int jsfe_profile_read(jsfe_handle* h, float* stage_ms, int64_t* stage_launches, int n_stages);
 /* number of kernels the library has launched since creation (bench.py's gpu_launches) */

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jsfe.h"
@@ -83,7 +84,10 @@ struct jsfe_handle {
     void (*fast_kernel)(jsfe::Params, jsfe::TmaMaps, int) = nullptr;   // the k_fast_cells<compass mode, mask> instance of this handle
     std::vector<void*> dev_allocs;
     // pinned staging for jsfe_download_results / jsfe_get_*
-    int32_t* h_n = nullptr;
+    uint8_t* d_arena = nullptr;    // n_kp | kps | desc | u_right | depth of every slot (one allocation; Params points into it)
+    uint8_t* h_arena = nullptr;    // the pinned mirror, same offsets
+    size_t arena_off[5] = {0, 0, 0, 0, 0}, arena_bytes = 0;
+    int32_t* h_n = nullptr;        // views into h_arena
     int32_t* h_kps = nullptr;
     uint8_t* h_desc = nullptr;
     float* h_ur = nullptr;
@@ -101,6 +105,7 @@ struct jsfe_handle {
     cudaStream_t st_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_blur = 1;
+    bool pdl = true;      // programmatic dependent launch between the kernels of the chain (JSFE_NO_PDL=1: plain launches)
     uint8_t* d_stage = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;
@@ -151,6 +156,23 @@ struct StageTimer {
         if (a) { cudaEvent_t b = take_event(h); cudaEventRecord(b, st); h->spans.push_back({stage, a, b}); }
     }
 };
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the stream is still
+// running; every kernel launched this way executes griddepcontrol.wait before it touches global memory (jsfe_kernels.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 int post_launch(jsfe_handle* h, const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -270,15 +292,6 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         P.blur_item_start[i + 1] = P.blur_item_start[i] + items;
     }
     P.blur_items_total = P.blur_item_start[P.L];
-    P.fix_item_start[0] = 0;
-    for (int i = 0; i < P.L; ++i) {
-        jsfe::LevelGeom& g = P.lv[i];
-        const int ncg = g.w > 2 * JSFE_B ? (g.w - 2 * JSFE_B + 3) / 4 : 0, rows = std::max(0, g.h - 2 * JSFE_B);
-        g.amb_pitch = (int)align_up(std::max(ncg, 1), 16);
-        g.amb_stride = align_up((size_t)g.amb_pitch * std::max(rows, 1), 256);
-        P.fix_item_start[i + 1] = P.fix_item_start[i] + (ncg ? (g.amb_pitch / 16) * rows : 0);
-    }
-    P.fix_items_total = P.fix_item_start[P.L];
     P.fast_items_total = items;
     P.cap = cells;
     P.n_tile_rows = tile_rows;
@@ -430,7 +443,6 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         jsfe::LevelGeom& g = P.lv[i];
         if ((rc = dev_alloc(h, &g.img, g.slot_stride * M)) != JSFE_OK) return bail(rc);
         if ((rc = dev_alloc(h, &g.blur, g.slot_stride * M)) != JSFE_OK) return bail(rc);  // stays 0 outside the blurred interior
-        if ((rc = dev_alloc(h, &g.amb, g.amb_stride * M)) != JSFE_OK) return bail(rc);    // pad bytes stay 0
         g.mask = nullptr;
         if (cfg->mask) {  // INTER_NEAREST + THRESH_BINARY(10), orb_gpu.cpp:78-90
             std::vector<uint8_t> m((size_t)g.h * g.pitch, 0);
@@ -477,15 +489,44 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     // ---- per-slot arrays
     if ((rc = dev_alloc(h, &P.cell_x, M * cap)) || (rc = dev_alloc(h, &P.cell_y, M * cap)) || (rc = dev_alloc(h, &P.cell_s, M * cap)) ||
         (rc = dev_alloc(h, &P.kp_x, M * cap)) || (rc = dev_alloc(h, &P.kp_y, M * cap)) || (rc = dev_alloc(h, &P.kp_s, M * cap)) ||
-        (rc = dev_alloc(h, &P.kp_l, M * cap)) || (rc = dev_alloc(h, &P.kp_angle, M * cap)) || (rc = dev_alloc(h, &P.n_kp, M)) ||
+        (rc = dev_alloc(h, &P.kp_l, M * cap)) || (rc = dev_alloc(h, &P.kp_angle, M * cap)) ||
         (rc = dev_alloc(h, &P.n_per_level, M * JSFE_MAXL)) || (rc = dev_alloc(h, &P.row_start, M * (size_t)(tile_rows + 1))) ||
-        (rc = dev_alloc(h, &P.kps, M * 6 * cap)) || (rc = dev_alloc(h, &P.desc, M * cap * 32)) ||
-        (rc = dev_alloc(h, &P.u_right, M * cap)) || (rc = dev_alloc(h, &P.depth, M * cap)) ||
         (rc = dev_alloc(h, &P.best_idx, M * cap)) || (rc = dev_alloc(h, &P.best_dist, M * cap)) ||
         (rc = dev_alloc(h, &P.sad_best, M * cap)))
         return bail(rc);
+    {   // the five result arrays a caller downloads live in ONE arena (device and pinned host, same offsets), so that the results
+        // of the whole handle -- the single-pair latency path -- cross PCIe as one copy instead of five
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+        h->arena_off[0] = carve(M * 4);
+        h->arena_off[1] = carve(M * 6 * cap * 4);
+        h->arena_off[2] = carve(M * cap * 32);
+        h->arena_off[3] = carve(M * cap * 4);
+        h->arena_off[4] = carve(M * cap * 4);
+        h->arena_bytes = off;
+        uint8_t* d = nullptr;
+        if ((rc = dev_alloc(h, &d, off)) != JSFE_OK) return bail(rc);
+        h->d_arena = d;
+        P.n_kp = (int*)(d + h->arena_off[0]);
+        P.kps = (int*)(d + h->arena_off[1]);
+        P.desc = d + h->arena_off[2];
+        P.u_right = (float*)(d + h->arena_off[3]);
+        P.depth = (float*)(d + h->arena_off[4]);
+    }
     P.blur_amb_units = JSFE_BLUR_AMB_UNITS;
-    if (const char* e = getenv("JSFE_DEBUG_BLUR_UNITS")) P.blur_amb_units = (unsigned)atoi(e);   // experiments only: < 3 breaks exactness
+    if (const char* e = getenv("JSFE_DEBUG_BLUR_UNITS")) P.blur_amb_units = (unsigned)atoi(e);   // experiments only: < 18 breaks exactness
+    if (cfg->apply_nms_ms && P.L > 1 && !cfg->nms_ms_mode_gpu) {
+        // k_nms_ms_buckets walks at most 64 candidates per level-0 bucket (the reference's host rule has no cap,
+        // orb_FAST_apply_NMS_MS.cpp:15-122).  A bucket is tile_h0 x tile_w0 level-0 pixels; level l has one candidate per cell of
+        // c_l = tile_l * scale_l level-0 pixels, and an interval of tile_0 pixels meets at most floor((tile_0 - 1) / c_l) + 2 such cells per axis.
+        // Geometries whose bound exceeds the scratch are refused instead of silently diverging.
+        long bound = 0;
+        for (int i = 0; i < P.L; ++i) {
+            const double ch = (double)P.lv[i].tile_h * P.lv[i].scale, cw = (double)P.lv[i].tile_w * P.lv[i].scale;
+            bound += (long)(std::floor((P.lv[0].tile_h - 1) / ch) + 2) * (long)(std::floor((P.lv[0].tile_w - 1) / cw) + 2);
+        }
+        if (bound > 64) return bail(fail(JSFE_ERR_INVALID, "cross-scale NMS (CPU rule): up to %ld candidates per level-0 bucket, the kernel holds 64", bound));
+    }
     if (cfg->apply_nms_ms && P.L > 1) {
         int ts = 64;
         while (ts < 2 * P.cap) ts <<= 1;
@@ -498,13 +539,14 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
             return bail(fail(JSFE_ERR_CUDA, "k_nms_ms_buckets needs %d bytes of shared memory", P.cap * 4));
     }
     // ---- pinned staging
-    if (cudaMallocHost((void**)&h->h_n, M * sizeof(int32_t)) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_kps, M * 6 * cap * sizeof(int32_t) + 16) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_desc, M * cap * 32 + 16) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_ur, M * cap * sizeof(float) + 16) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_dp, M * cap * sizeof(float) + 16) != cudaSuccess ||
+    if (cudaMallocHost((void**)&h->h_arena, h->arena_bytes + 16) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_misc, 5 * cap * sizeof(int32_t) + 16) != cudaSuccess)
         return bail(fail(JSFE_ERR_CUDA, "pinned host allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    h->h_n = (int32_t*)(h->h_arena + h->arena_off[0]);
+    h->h_kps = (int32_t*)(h->h_arena + h->arena_off[1]);
+    h->h_desc = h->h_arena + h->arena_off[2];
+    h->h_ur = (float*)(h->h_arena + h->arena_off[3]);
+    h->h_dp = (float*)(h->h_arena + h->arena_off[4]);
     {
         using jsfe::k_fast_cells;
         void (*const table[4][2])(jsfe::Params, jsfe::TmaMaps, int) = {
@@ -529,6 +571,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         if (const char* e = getenv("JSFE_CHUNK_IMAGES")) h->chunk_images = atoi(e);
     }
     if (const char* e = getenv("JSFE_NO_OVERLAP")) h->overlap_blur = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("JSFE_NO_PDL")) h->pdl = atoi(e) == 0;
     if (const char* e = getenv("JSFE_NO_REPITCH_KERNEL")) h->repitch_kernel = atoi(e) == 0;
     if (cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -556,11 +599,7 @@ int jsfe_destroy(jsfe_handle* h) {
     if (h->st_comp) cudaStreamDestroy(h->st_comp);
     if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->h_n) cudaFreeHost(h->h_n);
-    if (h->h_kps) cudaFreeHost(h->h_kps);
-    if (h->h_desc) cudaFreeHost(h->h_desc);
-    if (h->h_ur) cudaFreeHost(h->h_ur);
-    if (h->h_dp) cudaFreeHost(h->h_dp);
+    if (h->h_arena) cudaFreeHost(h->h_arena);
     if (h->h_misc) cudaFreeHost(h->h_misc);
     delete h;
     return JSFE_OK;
@@ -589,10 +628,9 @@ int jsfe_set_images(jsfe_handle* h, int first_slot, int n, const uint8_t* src, i
     if (src_is_device && row_pitch == g.w && h->repitch_kernel) {
         // contiguous rows on the device (the staging buffer of jsfe_process_host_pairs, or any packed device frame)
         const int chunks = g.h * (g.pitch / 16);
-        jsfe::k_repitch<<<dim3((chunks + 255) / 256, n), 256, 0, (cudaStream_t)stream>>>(
-            src, (long long)row_pitch, (long long)image_stride, src, src + (size_t)(n - 1) * image_stride + (size_t)g.h * row_pitch,
-            g.img + (size_t)first_slot * g.slot_stride, g.pitch, g.slot_stride, g.h, g.w);
-        CU(cudaGetLastError());
+        CU(launch_k(h->pdl, jsfe::k_repitch, dim3((chunks + 255) / 256, n), dim3(256), 0, (cudaStream_t)stream, src, (long long)row_pitch,
+                    (long long)image_stride, src, src + (size_t)(n - 1) * image_stride + (size_t)g.h * row_pitch,
+                    g.img + (size_t)first_slot * g.slot_stride, g.pitch, (unsigned long long)g.slot_stride, g.h, g.w));
         return JSFE_OK;
     }
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -637,7 +675,8 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     const jsfe::Params& P = h->P;
     if (P.pyr_blocks_total > 0) {
         StageTimer t(h, st, 0);
-        jsfe::k_pyramid<<<dim3(P.pyr_blocks_total, n), 256, 0, st>>>(P, first_slot);
+        const bool pdl = h->pdl && !h->profiling;
+        CU(launch_k(pdl, jsfe::k_pyramid, dim3(P.pyr_blocks_total, n), dim3(256), 0, st, P, first_slot));
         if ((rc = post_launch(h, "k_pyramid"))) return rc;
     }
     // fork: the blur of every level depends only on the pyramid, not on FAST; when profiling per kernel, stay serial
@@ -649,7 +688,7 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
     }
     {
         StageTimer t(h, st, 1);
-        h->fast_kernel<<<dim3(P.fast_items_total, n), 256, h->fast_smem, st>>>(P, h->tma, first_slot);
+        CU(launch_k(h->pdl && !h->profiling, h->fast_kernel, dim3(P.fast_items_total, n), dim3(256), h->fast_smem, st, P, h->tma, first_slot));
     }
     if ((rc = post_launch(h, "k_fast_cells"))) return rc;
     if (P.blur_items_total > 0) {
@@ -658,30 +697,26 @@ static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream) {
             jsfe::k_blur<<<dim3((P.blur_items_total + 255) / 256, n), 256, 0, sb>>>(P, first_slot);
         }
         if ((rc = post_launch(h, "k_blur"))) return rc;
-        {
-            StageTimer t(h, sb, 8);
-            jsfe::k_blur_fix<<<dim3((P.fix_items_total + 1023) / 1024, n), 256, 0, sb>>>(P, first_slot);
-        }
-        if ((rc = post_launch(h, "k_blur_fix"))) return rc;
         if (overlap) CU(cudaEventRecord(h->ev_join, sb));
     }
     if (h->cfg.apply_nms_ms && P.L > 1) {  // orb_gpu.cpp:665-712
         {
             StageTimer t(h, st, 6);
-            if (h->cfg.nms_ms_mode_gpu) jsfe::k_nms_ms_dense<<<n, 1024, 0, st>>>(P, first_slot);
-            else jsfe::k_nms_ms_buckets<<<n, 256, (size_t)P.cap * 4, st>>>(P, first_slot);
+            if (h->cfg.nms_ms_mode_gpu) CU(launch_k(h->pdl && !h->profiling, jsfe::k_nms_ms_dense, dim3(n), dim3(1024), 0, st, P, first_slot));
+            else CU(launch_k(h->pdl && !h->profiling, jsfe::k_nms_ms_buckets, dim3(n), dim3(256), (size_t)P.cap * 4, st, P, first_slot));
         }
         if ((rc = post_launch(h, "k_nms_ms"))) return rc;
     }
     {
         StageTimer t(h, st, 2);
-        jsfe::k_compact<<<n, 1024, 0, st>>>(P, first_slot);
+        CU(launch_k(h->pdl && !h->profiling, jsfe::k_compact, dim3(n), dim3(1024), 0, st, P, first_slot));
     }
     if ((rc = post_launch(h, "k_compact"))) return rc;
     if (overlap) CU(cudaStreamWaitEvent(st, h->ev_join, 0));   // join: the descriptor samples the blurred levels
     {
         StageTimer t(h, st, 3);
-        jsfe::k_orient_desc<<<dim3((P.cap + 8 * JSFE_KP_PER_WARP - 1) / (8 * JSFE_KP_PER_WARP), n), 256, 0, st>>>(P, h->tma, first_slot);
+        CU(launch_k(h->pdl && !h->profiling, jsfe::k_orient_desc, dim3((P.cap + 8 * JSFE_KP_PER_WARP - 1) / (8 * JSFE_KP_PER_WARP), n), dim3(256), 0,
+                    st, P, h->tma, first_slot));
     }
     if ((rc = post_launch(h, "k_orient_desc"))) return rc;
     return JSFE_OK;
@@ -704,11 +739,11 @@ int launch_stereo(jsfe_handle* h, const jsfe::RightSide& r, int first_pair, int 
     const jsfe::Params& P = h->P;
     {
         StageTimer t(h, st, 4);
-        jsfe::k_stereo_match<<<dim3((P.cap + 7) / 8, n), 256, 0, st>>>(P, r, first_pair, th_high, th_low, mb, mbf);
+        CU(launch_k(h->pdl && !h->profiling, jsfe::k_stereo_match, dim3((P.cap + 7) / 8, n), dim3(256), 0, st, P, r, first_pair, th_high, th_low, mb, mbf));
     }
     if ((rc = post_launch(h, "k_stereo_match"))) return rc;
     StageTimer t(h, st, 5);
-    jsfe::k_stereo_outlier<<<n, 1024, 0, st>>>(P, first_pair, r.left_mul, r.left_add);
+    CU(launch_k(h->pdl && !h->profiling, jsfe::k_stereo_outlier, dim3(n), dim3(1024), 0, st, P, first_pair, r.left_mul, r.left_add));
     return post_launch(h, "k_stereo_outlier");
 }
 }  // namespace
@@ -781,6 +816,20 @@ int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t*
         jsfe::k_pack<<<(8 * n + 255) / 256, 256, 0, st>>>(h->P, slot, n, dst_kps_dev, dst_desc_dev);
         if ((rc = post_launch(h, "k_pack"))) return rc;
     }
+    return JSFE_OK;
+}
+
+int jsfe_pack_keypoints_once(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out, void* stream) {
+    int rc = check_slots(h, slot, 1);
+    if (rc) return rc;
+    if (!dst_kps_dev || !dst_desc_dev || !n_out) return fail(JSFE_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    jsfe::k_pack<<<(8 * h->P.cap + 255) / 256, 256, 0, st>>>(h->P, slot, -1, dst_kps_dev, dst_desc_dev);
+    if ((rc = post_launch(h, "k_pack"))) return rc;
+    CU(cudaMemcpyAsync(h->h_n, h->P.n_kp + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = h->h_n[0];
     return JSFE_OK;
 }
 
@@ -935,6 +984,10 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
         ~ProfilingOff() { h->profiling = saved; }
     } profiling_off(h);
     auto enqueue_results = [&](int s0, int ns, cudaStream_t st) -> int {
+        if (s0 == 0 && ns == h->max_images) {   // the whole handle (the single-pair latency path): one copy of the result arena
+            CU(cudaMemcpyAsync(h->h_arena, h->d_arena, h->arena_bytes, cudaMemcpyDeviceToHost, st));
+            return JSFE_OK;
+        }
         CU(cudaMemcpyAsync(h->h_n + s0, P.n_kp + s0, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->h_kps + (size_t)s0 * 6 * cap, P.kps + (size_t)s0 * 6 * cap, (size_t)ns * 6 * cap * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->h_desc + (size_t)s0 * cap * 32, P.desc + (size_t)s0 * cap * 32, (size_t)ns * cap * 32, cudaMemcpyDeviceToHost, st));
@@ -1130,13 +1183,14 @@ int jsfe_remap_bilinear(const uint8_t* src, int src_h, int src_w, int64_t src_pi
         return fail(JSFE_ERR_INVALID, "bad argument");
     if (n_images == 0) return JSFE_OK;
     const int word_stores = ((uintptr_t)dst % 4 == 0) && (dst_pitch % 4 == 0) && (dst_stride % 4 == 0);
+    const int word_loads = ((uintptr_t)src % 4 == 0) && (src_pitch % 4 == 0) && (src_stride % 4 == 0);   // the window path reads aligned words
     // images in flight per output tile: enough blocks to fill the GPU, few enough that the decoded maps are reused
     const int tiles = ((dst_w + 255) / 256) * ((dst_h + 3) / 4);
     const int groups = (n_images + JSFE_REMAP_UNROLL - 1) / JSFE_REMAP_UNROLL;   // a thread handles its images JSFE_REMAP_UNROLL at a time
     const int gz = std::max(1, std::min(groups, (148 * 8 + tiles - 1) / tiles));
     jsfe::k_remap_bilinear<<<dim3((dst_w + 255) / 256, (dst_h + 3) / 4, gz), 256, 0, (cudaStream_t)stream>>>(
         src, src_h, src_w, (long long)src_pitch, (long long)src_stride, n_images, map_x, map_y, dst_h, dst_w, dst, (long long)dst_pitch,
-        (long long)dst_stride, word_stores);
+        (long long)dst_stride, word_stores, word_loads);
     CU(cudaGetLastError());
     return JSFE_OK;
 }

@@ -38,6 +38,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// ---- programmatic dependent launch (sm_90+): every kernel of the per-frame chain lets its successor in the stream start as soon as
+// all of its own blocks are running (launch_dependents at entry) and itself waits for the completion -- and the memory -- of its
+// predecessor right before it first touches global memory.  Between the 8 small kernels of a single stereo pair this hides the
+// launch latency of each edge; launched without the attribute (or behind a copy / an event) both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // =================================================================================================
 // K1  k_pyramid: every level l >= 1 is a bilinear resample of level 0.
 //     replaces imresize_GPU_pitched (src/cuda/orb_pyramid.cu:18-68): one launch for all levels and all
@@ -55,6 +62,8 @@ __device__ __forceinline__ float u8_to_f32(unsigned v) { return __uint_as_float(
 __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ src, long long src_row_pitch, long long src_image_stride,
                                                  const uint8_t* __restrict__ src_begin, const uint8_t* __restrict__ src_end, uint8_t* __restrict__ dst, int pitch,
                                                  unsigned long long slot_stride, int h, int w) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cpr = pitch >> 4;                                   // chunks per row
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= h * cpr) return;
@@ -89,7 +98,9 @@ __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ src
 #define JSFE_PYR_ROWS 32   // rows per block tile (8 y-lanes x 4 rows each)
 
 __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params p, int slot0) {
-    const uint32_t item = __ldg(p.pyr_map + blockIdx.x);   // level << 28 | tile row << 14 | tile column
+    pdl_launch_dependents();
+    const uint32_t item = __ldg(p.pyr_map + blockIdx.x);   // level << 28 | tile row << 14 | tile column (a table written at create time)
+    pdl_wait();
     const int l = (int)(item >> 28);
     const LevelGeom& lv = p.lv[l];
     const int slot = slot0 + blockIdx.y;
@@ -256,6 +267,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     __shared__ __align__(16) int s_npos[8];   // positives per warp (each warp owns an eighth of the positives area: no atomics, and
                                               // phase C walks a warp's own segment); -1 = that segment overflowed
     constexpr int PW = JSFE_FAST_PW;
+    pdl_launch_dependents();
     const uint32_t item = __ldg(p.fast_map + blockIdx.x);   // level << 28 | tile row << 14 | block in row
     const int l = (int)(item >> 28);
     const LevelGeom& lv = p.lv[l];
@@ -283,6 +295,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int xlo = max(X0 - 1, JSFE_B), xhi = min(X0 + GW, lv.w - JSFE_B - 1);  // inclusive valid x range
 
     // ---- stage the pixel tile: one TMA box load (out-of-image rows/columns arrive as 0); meanwhile clear the scores
+    pdl_wait();                           // the level images are the predecessor's output
     if (p.use_tma) {
         if (tid == 0) {
             mbar_init(&s_bar, 1);
@@ -531,15 +544,20 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
 //
 //  The reference's value is trunc(chain of 49 sequential FFMA).  We evaluate the separable form
 //  (7+7 FFMA per pixel; one thread owns 4 columns x 32 rows and keeps the row sums of the last 7 input rows
-//  in a rotating register window), whose distance to the chain is bounded by 5.3e-4 (DESIGN.md section 4);
-//  when the separable value lies within 6e-4 of an integer the exact chain is evaluated instead, so the
-//  stored byte is always the reference's.  No shared memory: input words come through L1 (each 32-bit word
-//  of a row is shared by 3 neighbouring threads), bytes are widened with PRMT + FADD (0x4B000000 trick).
+//  in a rotating register window), whose distance to the chain is bounded by 5.3e-4 (DESIGN.md section 4.2);
+//  a pixel whose separable value lies within 18 x 2^-15 = 5.49e-4 of an integer is ambiguous and gets the
+//  exact chain instead, so the stored byte is always the reference's.  The ambiguity flags never leave the
+//  block: each thread keeps the 4-bit mask of every row it produced in its own 32 bytes of shared memory,
+//  after the strip loop the flagged pixels (about 0.1 % on textured images, all of a flat region) are
+//  compacted into a block-wide list and re-evaluated densely, one thread per listed pixel -- no mask in HBM,
+//  no second kernel, no atomics inside the FFMA loop.  Input words come through L1 (each 32-bit word of a row
+//  is shared by 3 neighbouring threads), bytes are widened with PRMT + FADD (0x4B000000 trick).
 // =================================================================================================
-#define JSFE_BLUR_AMB_UNITS 3u   // ambiguity margin of k_blur in units of 2^-12 (see the kernel)
+#define JSFE_BLUR_AMB_UNITS 18u   // ambiguity margin in units of 2^-15: 18 * 2^-15 = 5.49e-4 >= the 5.3e-4 bound on |separable - chain|
 #ifndef JSFE_BLUR_ROWS
 #define JSFE_BLUR_ROWS 32
 #endif
+#define JSFE_FIX_LIST 2048        // block-wide list of ambiguous pixels; beyond it (flat regions) the owner decides its pixels in place
 
 // separable factors of the 7x7 weights; the same for every handle (sigma is fixed at 10 in the reference), kept in
 // constant memory so the FFMAs read them as c[][] operands instead of holding 14 registers (74 -> ~60: 4 blocks/SM)
@@ -562,137 +580,124 @@ __device__ __forceinline__ float byte_f(unsigned w, unsigned sel) {   // exact u
 }
 
 __global__ void __launch_bounds__(256, 3) k_blur(const __grid_constant__ Params p, int slot0) {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= p.blur_items_total) return;
-    int l = 0;
-    while (l + 1 < p.L && gi >= p.blur_item_start[l + 1]) ++l;
-    const LevelGeom& lv = p.lv[l];
+    __shared__ __align__(16) uint8_t s_flag[256 * JSFE_BLUR_ROWS];   // [thread][row of its strip]: 4-bit ambiguity mask of its 4 pixels
+    __shared__ unsigned s_list[JSFE_FIX_LIST];                       // level << 28 | y << 14 | x
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
+    const int gi = blockIdx.x * blockDim.x + tid;
+    const bool active = gi < p.blur_items_total;
     const int slot = slot0 + blockIdx.y;
-    const int ncg = (lv.w - 2 * JSFE_B + 3) >> 2;               // 4-column groups over [20, w-20)
-    const int li = gi - p.blur_item_start[l];
-    const int strip = li / ncg, cg = li - strip * ncg;
-    const int xg = JSFE_B + (cg << 2);                           // 20 is a multiple of 4: groups are word-aligned
-    const int r0 = JSFE_B + strip * JSFE_BLUR_ROWS, r1 = min(r0 + JSFE_BLUR_ROWS, lv.h - JSFE_B);
-    const int xend = lv.w - JSFE_B;
-    const uint8_t* __restrict__ src = lv.img + (size_t)slot * lv.slot_stride;
-    uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
-    uint8_t* __restrict__ amap = lv.amb + (size_t)slot * lv.amb_stride;
-    const int nin = r1 - r0 + 6;                                 // input rows r0-3 .. r1+2
-    const uint8_t* rp = src + (size_t)(r0 - 3) * lv.pitch + xg;
-    float q[4][7];
-    for (int base = 0; base < nin; base += 7) {
-        // issue the loads of the next 7 input rows back to back (21 independent 32-bit loads in flight per thread):
-        // the rows arrive from L2/HBM while the other warps of the SM are in their FFMA phase
-        unsigned wr[7][3];
+    uint4* myflags = reinterpret_cast<uint4*>(s_flag + tid * JSFE_BLUR_ROWS);
+    myflags[0] = make_uint4(0, 0, 0, 0);
+    myflags[1] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) s_n = 0;
+    int l = 0, xg = 0, r0 = 0, xend = 0;
+    if (active) {
+        while (l + 1 < p.L && gi >= p.blur_item_start[l + 1]) ++l;
+        const LevelGeom& lv = p.lv[l];
+        const int ncg = (lv.w - 2 * JSFE_B + 3) >> 2;               // 4-column groups over [20, w-20)
+        const int li = gi - p.blur_item_start[l];
+        const int strip = li / ncg, cg = li - strip * ncg;
+        xg = JSFE_B + (cg << 2);                                     // 20 is a multiple of 4: groups are word-aligned
+        r0 = JSFE_B + strip * JSFE_BLUR_ROWS;
+        const int r1 = min(r0 + JSFE_BLUR_ROWS, lv.h - JSFE_B);
+        xend = lv.w - JSFE_B;
+        const uint8_t* __restrict__ src = lv.img + (size_t)slot * lv.slot_stride;
+        uint8_t* __restrict__ dst = lv.blur + (size_t)slot * lv.slot_stride;
+        uint8_t* fl = s_flag + tid * JSFE_BLUR_ROWS;
+        const int nin = r1 - r0 + 6;                                 // input rows r0-3 .. r1+2
+        const uint8_t* rp = src + (size_t)(r0 - 3) * lv.pitch + xg;
+        float q[4][7];
+        for (int base = 0; base < nin; base += 7) {
+            // issue the loads of the next 7 input rows back to back (21 independent 32-bit loads in flight per thread):
+            // the rows arrive from L2/HBM while the other warps of the SM are in their FFMA phase
+            unsigned wr[7][3];
 #pragma unroll
-        for (int ph = 0; ph < 7; ++ph) {
-            if (base + ph < nin) {
-                const uint8_t* r = rp + (size_t)ph * lv.pitch;
-                wr[ph][0] = __ldg(reinterpret_cast<const unsigned*>(r - 4));
-                wr[ph][1] = __ldg(reinterpret_cast<const unsigned*>(r));
-                wr[ph][2] = __ldg(reinterpret_cast<const unsigned*>(r + 4));
-            }
-        }
-        rp += (size_t)7 * lv.pitch;
-#pragma unroll
-        for (int ph = 0; ph < 7; ++ph) {
-            const int ir = base + ph;
-            if (ir < nin) {
-                const unsigned W0 = wr[ph][0], W1 = wr[ph][1], W2 = wr[ph][2];
-                float f[10];  // pixels xg-3 .. xg+6
-                f[0] = byte_f(W0, 0x7441); f[1] = byte_f(W0, 0x7442); f[2] = byte_f(W0, 0x7443);
-                f[3] = byte_f(W1, 0x7440); f[4] = byte_f(W1, 0x7441); f[5] = byte_f(W1, 0x7442); f[6] = byte_f(W1, 0x7443);
-                f[7] = byte_f(W2, 0x7440); f[8] = byte_f(W2, 0x7441); f[9] = byte_f(W2, 0x7442);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float r = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) r = __fmaf_rn(c_sep_b[j], f[k + j], r);
-                    q[k][ph] = r;
+            for (int ph = 0; ph < 7; ++ph) {
+                if (base + ph < nin) {
+                    const uint8_t* r = rp + (size_t)ph * lv.pitch;
+                    wr[ph][0] = __ldg(reinterpret_cast<const unsigned*>(r - 4));
+                    wr[ph][1] = __ldg(reinterpret_cast<const unsigned*>(r));
+                    wr[ph][2] = __ldg(reinterpret_cast<const unsigned*>(r + 4));
                 }
-                if (ir >= 6) {
-                    const int y = r0 + ir - 6;
-                    unsigned out = 0, amb = 0;
+            }
+            rp += (size_t)7 * lv.pitch;
+#pragma unroll
+            for (int ph = 0; ph < 7; ++ph) {
+                const int ir = base + ph;
+                if (ir < nin) {
+                    const unsigned W0 = wr[ph][0], W1 = wr[ph][1], W2 = wr[ph][2];
+                    float f[10];  // pixels xg-3 .. xg+6
+                    f[0] = byte_f(W0, 0x7441); f[1] = byte_f(W0, 0x7442); f[2] = byte_f(W0, 0x7443);
+                    f[3] = byte_f(W1, 0x7440); f[4] = byte_f(W1, 0x7441); f[5] = byte_f(W1, 0x7442); f[6] = byte_f(W1, 0x7443);
+                    f[7] = byte_f(W2, 0x7440); f[8] = byte_f(W2, 0x7441); f[9] = byte_f(W2, 0x7442);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        float A = 0.0f;
+                        float r = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 7; ++j) A = __fmaf_rn(c_sep_a[j], q[k][(ph + 1 + j) % 7], A);
-                        // A in [0, 256): RZ(A + 2048) = 2048 + floor(A * 4096) / 4096, so bits 12..19 of the sum are trunc(A) and
-                        // bits 0..11 the fraction in units of 2^-12.  Within blur_amb_units (3 units = 7.3e-4 > the 5.3e-4 bound on
-                        // |A - E|) of an integer the truncation of the reference's chain E may differ: flag it.
-                        const unsigned tb = __float_as_uint(__fadd_rz(A, 2048.0f));
-                        amb |= (((tb + p.blur_amb_units) & 0xFFFu) < 2u * p.blur_amb_units ? 1u : 0u) << k;
-                        out |= ((tb >> 12) & 0xFFu) << (8 * k);
+                        for (int j = 0; j < 7; ++j) r = __fmaf_rn(c_sep_b[j], f[k + j], r);
+                        q[k][ph] = r;
                     }
-                    // pixels that close to an integer (about 0.15 % on textured images, all of a flat region) are decided
-                    // by the exact chain in k_blur_fix; here only their 4-bit mask is recorded (dense, no atomics)
-                    amap[(size_t)(y - JSFE_B) * lv.amb_pitch + cg] = (uint8_t)amb;
-                    uint8_t* o = dst + (size_t)y * lv.pitch + xg;
-                    if (xg + 3 < xend) {
-                        *reinterpret_cast<unsigned*>(o) = out;
-                    } else {
+                    if (ir >= 6) {
+                        const int y = r0 + ir - 6;
+                        unsigned out = 0, amb = 0;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (xg + k < xend) o[k] = (uint8_t)(out >> (8 * k));
+                        for (int k = 0; k < 4; ++k) {
+                            float A = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 7; ++j) A = __fmaf_rn(c_sep_a[j], q[k][(ph + 1 + j) % 7], A);
+                            // A in [0, 256): RZ(A + 256) = 256 + floor(A * 2^15) / 2^15, so mantissa bits 15..22 are trunc(A) and bits
+                            // 0..14 the fraction in units of 2^-15.  Within blur_amb_units of an integer the truncation of the
+                            // reference's chain E may differ from trunc(A) (|A - E| <= 5.3e-4): flag the pixel.
+                            const unsigned tb = __float_as_uint(__fadd_rz(A, 256.0f));
+                            amb |= (((tb + p.blur_amb_units) & 0x7FFFu) < 2u * p.blur_amb_units ? 1u : 0u) << k;
+                            out |= ((tb >> 15) & 0xFFu) << (8 * k);
+                        }
+                        fl[y - r0] = (uint8_t)amb;
+                        uint8_t* o = dst + (size_t)y * lv.pitch + xg;
+                        if (xg + 3 < xend) {
+                            *reinterpret_cast<unsigned*>(o) = out;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (xg + k < xend) o[k] = (uint8_t)(out >> (8 * k));
+                        }
                     }
                 }
             }
         }
     }
-}
-
-// K2d k_blur_fix: scans the ambiguity masks written by k_blur (16 mask bytes = 64 pixels per load; almost all zero),
-//     compacts the flagged pixels of the block into a shared-memory list and gives each of them the reference's exact
-//     49-FFMA chain, one thread per listed pixel (dense).  When the list is full (flat regions flag whole rows) the
-//     remaining pixels are decided in place -- whole warps are busy then anyway.
-#define JSFE_FIX_VEC 4       // mask vectors per thread
-#define JSFE_FIX_LIST 2048
-__global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ Params p, int slot0) {
-    __shared__ unsigned s_list[JSFE_FIX_LIST];
-    __shared__ int s_n;
-    const int slot = slot0 + blockIdx.y;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
+    __syncthreads();          // s_n = 0 is visible; the separable bytes of this block are ordered before the corrections below
+    if (active) {
+        const uint4 fa = myflags[0], fb = myflags[1];
+        if (fa.x | fa.y | fa.z | fa.w | fb.x | fb.y | fb.z | fb.w) {
+            const LevelGeom& lv = p.lv[l];
+            const unsigned* fw = reinterpret_cast<const unsigned*>(myflags);
 #pragma unroll 1
-    for (int q = 0; q < JSFE_FIX_VEC; ++q) {
-        const int gi = (blockIdx.x * JSFE_FIX_VEC + q) * 256 + threadIdx.x;
-        if (gi >= p.fix_items_total) break;
-        int l = 0;
-        while (l + 1 < p.L && gi >= p.fix_item_start[l + 1]) ++l;
-        const LevelGeom& lv = p.lv[l];
-        const int vpr = lv.amb_pitch >> 4;                            // uint4 vectors per mask row
-        const int li = gi - p.fix_item_start[l];
-        const int row = li / vpr, v = li - row * vpr;
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(lv.amb + (size_t)slot * lv.amb_stride + (size_t)row * lv.amb_pitch) + v);
-        if ((m.x | m.y | m.z | m.w) == 0u) continue;
-        // 16 mask bytes (low nibble = 4 pixels each) -> one 64-bit pixel mask; then visit only the set bits
-        auto squeeze = [](unsigned w) -> unsigned long long {
-            return (unsigned long long)((w & 0xFu) | ((w >> 4) & 0xF0u) | ((w >> 8) & 0xF00u) | ((w >> 12) & 0xF000u));
-        };
-        unsigned long long bits = squeeze(m.x) | (squeeze(m.y) << 16) | (squeeze(m.z) << 32) | (squeeze(m.w) << 48);
-        const int y = JSFE_B + row;
-        const int xbase = JSFE_B + (v << 6);
-        while (bits) {
-            const int b = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            const int x = xbase + b;
-            if (x >= lv.w - JSFE_B) break;            // pad columns of the last group (higher bits are further right)
-            const int pos = atomicAdd(&s_n, 1);
-            if (pos < JSFE_FIX_LIST) {
-                s_list[pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)x;
-            } else {
-                const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
-                lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
+            for (int k = 0; k < 8; ++k) {
+                unsigned m = fw[k] & 0x0F0F0F0Fu;                // byte j = row 4k + j, low nibble = its 4 pixels
+                while (m) {
+                    const int b = __ffs((int)m) - 1;
+                    m &= m - 1;
+                    const int y = r0 + 4 * k + (b >> 3), x = xg + (b & 7);
+                    if (x >= xend) continue;                      // pad columns of the last group
+                    const int pos = atomicAdd(&s_n, 1);
+                    if (pos < JSFE_FIX_LIST) {
+                        s_list[pos] = ((unsigned)l << 28) | ((unsigned)y << 14) | (unsigned)x;
+                    } else {                                       // list full (flat region: every lane is here): decide in place
+                        const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
+                        lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
+                    }
+                }
             }
         }
     }
     __syncthreads();
     const int n = min(s_n, JSFE_FIX_LIST);
-    for (int i = threadIdx.x; i < n; i += 256) {
+    for (int i = tid; i < n; i += 256) {
         const unsigned code = s_list[i];
-        const int l = code >> 28, y = (code >> 14) & 0x3FFF, x = code & 0x3FFF;
-        const LevelGeom& lv = p.lv[l];
+        const int ll = code >> 28, y = (code >> 14) & 0x3FFF, x = code & 0x3FFF;
+        const LevelGeom& lv = p.lv[ll];
         const size_t o = (size_t)slot * lv.slot_stride + (size_t)y * lv.pitch + x;
         lv.blur[o] = (uint8_t)blur_exact(lv.img + o, lv.pitch, p.tab->gauss);
     }
@@ -716,6 +721,8 @@ __global__ void __launch_bounds__(256) k_blur_fix(const __grid_constant__ Params
 __device__ __forceinline__ unsigned hash_px(int key) { return (unsigned)key * 2654435761u; }
 
 __global__ void __launch_bounds__(1024) k_nms_ms_dense(const __grid_constant__ Params p, int slot0) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int slot = slot0 + blockIdx.x;
     const int ts = p.ms_table_size, mask = ts - 1;
     int* keys = p.ms_keys + (size_t)slot * ts;
@@ -774,6 +781,8 @@ __global__ void __launch_bounds__(1024) k_nms_ms_dense(const __grid_constant__ P
 }
 
 __global__ void __launch_bounds__(256) k_nms_ms_buckets(const __grid_constant__ Params p, int slot0) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ int s_bucket[];  // bucket id per cell (-1: no candidate)
     const int slot = slot0 + blockIdx.x;
     int* cs = p.cell_s + (size_t)slot * p.cap;
@@ -824,6 +833,8 @@ __global__ void __launch_bounds__(256) k_nms_ms_buckets(const __grid_constant__ 
 //     Also records, for the stereo matcher, the first keypoint index of every (level, tile row).
 // =================================================================================================
 __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params p, int slot0) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int warp_tot[32];
     __shared__ int s_base;
     const int slot = slot0 + blockIdx.x;
@@ -911,6 +922,8 @@ __global__ void __launch_bounds__(1024) k_compact(const __grid_constant__ Params
 #endif
 
 __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm, int slot0) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(128) uint8_t s_buf[8][JSFE_WARP_SMEM];
     __shared__ __align__(8) uint64_t s_bar[8];
     __shared__ float2 s_pat[512];                    // rBRIEF sample offsets as floats (x, y)
@@ -1041,6 +1054,8 @@ __global__ void __launch_bounds__(256) k_orient_desc(const __grid_constant__ Par
 #endif
 __global__ void __launch_bounds__(256, JSFE_SM_BLOCKS) k_stereo_match(const __grid_constant__ Params p, const __grid_constant__ RightSide rsd,
                                                       int pair0, int th_high, int th_low, float mb, float mbf) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int pair = pair0 + blockIdx.y;
     const int sl = rsd.left_mul * pair + rsd.left_add, sr = rsd.right_mul * pair + rsd.right_add;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1173,6 +1188,8 @@ __global__ void __launch_bounds__(256, JSFE_SM_BLOCKS) k_stereo_match(const __gr
 //     minimum is >= 1.5*1.4*median, median = element n/2 of the ascending list.  Two-pass 8-bit radix
 //     select in shared memory, one block per pair.
 __global__ void __launch_bounds__(1024) k_stereo_outlier(const __grid_constant__ Params p, int pair0, int left_mul, int left_add) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ int hist[256];
     __shared__ int s_n, s_hi, s_k2, s_med;
     const int sl = left_mul * (pair0 + blockIdx.x) + left_add;
@@ -1225,6 +1242,7 @@ __global__ void __launch_bounds__(1024) k_stereo_outlier(const __grid_constant__
 // K7  k_pack: reference output layout (6 planes with stride N, descriptors 32N) into caller buffers
 //     (src/cuda/orb_gpu.cpp:784-831); used by the C++ compat shim and jsfe_get_keypoints.
 __global__ void k_pack(const __grid_constant__ Params p, int slot, int n, int* dst_kps, uint8_t* dst_desc) {
+    if (n < 0) n = p.n_kp[slot];          // the count stays on the device: the caller learns it from the same stream later
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 6 * n && dst_kps) {
         const int plane = i / n, j = i - plane * n;
@@ -1487,24 +1505,32 @@ __global__ void __launch_bounds__(256) k_frame_view(const __grid_constant__ Para
 //                     Thread = 4 output pixels of one row; the decoded map entry (tap address, 4 weights) is reused for
 //                     every image of the batch (frames of one camera share the maps), so the 8 B/px of map traffic is
 //                     paid once per batch and each image costs ~1 B read (L2-gathered taps) + 1 B write per pixel.
+//                     Two per-thread paths, chosen once when the map entries are decoded:
+//                       window  (rectification-like maps: the 4 pixels read one source row pair, at most 7 columns apart, all taps
+//                                inside the image): per image 6 aligned 32-bit loads fetch a 12-byte window of both rows, two funnel
+//                                shifts per row align it to the first tap, PRMT picks each pixel's 2 x 2 bytes and two IDP.2A
+//                                (u16 x u8 dot products) apply the four weights -- 1.5 loads and ~8 ALU ops per pixel;
+//                       gather  (anything else: borders, row crossings, wild maps): four byte loads per pixel.
+//                     Both are the same integer arithmetic, i.e. bit-exact with OpenCV.
 //   k_cvt_gray        cv::cvtColor(*2GRAY) for 8-bit BGR/RGB(A) (src/Tracking.cpp:260-285): 15-bit coefficients.
 // =================================================================================================
 #ifndef JSFE_REMAP_UNROLL
-#define JSFE_REMAP_UNROLL 1   // images whose taps are loaded before any is used; measured on B200: 1 -> 0.58, 2 -> 0.6, 4 -> 1.1 us/image
+#define JSFE_REMAP_UNROLL 1   // gather path: images whose taps are loaded before any is used; measured on B200: 1 -> 0.58, 2 -> 0.6, 4 -> 1.1 us/image
 #endif                        // (752x480): the register cost of deeper unrolling outweighs the extra loads in flight
 __global__ void __launch_bounds__(256) k_remap_bilinear(const uint8_t* __restrict__ src, int src_h, int src_w, long long src_pitch,
                                                         long long src_stride, int n_images, const float* __restrict__ map_x,
                                                         const float* __restrict__ map_y, int dst_h, int dst_w,
                                                         uint8_t* __restrict__ dst, long long dst_pitch, long long dst_stride,
-                                                        int word_stores) {
+                                                        int word_stores, int word_loads) {
     const int x4 = (blockIdx.x * 64 + (threadIdx.x & 63)) << 2, y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x4 >= dst_w || y >= dst_h) return;
     long long off[4];      // offset of tap (iy, ix) in the source image (may point outside: guarded by the valid bits)
     unsigned w01[4], w23[4];   // packed int16 weights: (w00 | w01 << 16), (w10 | w11 << 16)
     unsigned valid = 0;    // 4 bits per pixel: tap k of pixel j inside the source
+    int ixs[4], iys[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        off[j] = 0; w01[j] = 0; w23[j] = 0;
+        off[j] = 0; w01[j] = 0; w23[j] = 0; ixs[j] = 0; iys[j] = 0;
         if (x4 + j < dst_w) {
             const size_t m = (size_t)y * dst_w + x4 + j;
             const int sx = __float2int_rn(__fmul_rn(__ldg(map_x + m), 32.0f)), sy = __float2int_rn(__fmul_rn(__ldg(map_y + m), 32.0f));
@@ -1514,12 +1540,42 @@ __global__ void __launch_bounds__(256) k_remap_bilinear(const uint8_t* __restric
             w01[j] = (unsigned)a | ((unsigned)b << 16);
             w23[j] = (unsigned)c | ((unsigned)d << 16);
             off[j] = (long long)iy * src_pitch + ix;
+            ixs[j] = ix; iys[j] = iy;
             const unsigned x0 = (unsigned)ix < (unsigned)src_w, x1 = (unsigned)(ix + 1) < (unsigned)src_w;
             const unsigned y0 = (unsigned)iy < (unsigned)src_h, y1 = (unsigned)(iy + 1) < (unsigned)src_h;
             valid |= ((x0 & y0) | ((x1 & y0) << 1) | ((x0 & y1) << 2) | ((x1 & y1) << 3)) << (4 * j);
         }
     }
-    // images in groups of JSFE_REMAP_UNROLL: all 16 x U tap loads are issued before the first is used
+    // window path: all 4 pixels present, every tap inside the image, one source row pair, columns within 7 of the leftmost tap, and
+    // the 12-byte window [base, base + 12) inside the row (base = leftmost tap rounded down to a word)
+    const int ixmin = min(min(ixs[0], ixs[1]), min(ixs[2], ixs[3])), ixmax = max(max(ixs[0], ixs[1]), max(ixs[2], ixs[3]));
+    const int wbase = ixmin & ~3;
+    const bool window = word_loads && word_stores && x4 + 3 < dst_w && valid == 0xFFFFu && iys[0] == iys[1] && iys[0] == iys[2] && iys[0] == iys[3] &&
+                        ixmax - ixmin <= 6 && wbase + 12 <= src_w;
+    if (window) {
+        const unsigned sh = (unsigned)(ixmin & 3) * 8u;
+        unsigned sel[4];      // PRMT selector of pixel j on the aligned 8-byte window: bytes (d, d+1), d = ix_j - ixmin
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const unsigned d = (unsigned)(ixs[j] - ixmin); sel[j] = d | ((d + 1u) << 4); }
+        const long long woff = (long long)iys[0] * src_pitch + wbase;
+        for (int img = blockIdx.z; img < n_images; img += gridDim.z) {
+            const unsigned* __restrict__ t = reinterpret_cast<const unsigned*>(src + (size_t)img * src_stride + woff);
+            const unsigned* __restrict__ b = reinterpret_cast<const unsigned*>(src + (size_t)img * src_stride + woff + src_pitch);
+            const unsigned t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+            const unsigned T0 = __funnelshift_r(t0, t1, sh), T1 = __funnelshift_r(t1, t2, sh);   // 8 bytes from the leftmost tap
+            const unsigned B0 = __funnelshift_r(b0, b1, sh), B1 = __funnelshift_r(b1, b2, sh);
+            unsigned out = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned taps = __byte_perm(__byte_perm(T0, T1, sel[j]), __byte_perm(B0, B1, sel[j]), 0x5410);   // p00 p01 p10 p11
+                const unsigned acc = __dp2a_hi(w23[j], taps, __dp2a_lo(w01[j], taps, 0u));
+                out |= min((acc + (1u << 14)) >> 15, 255u) << (8 * j);
+            }
+            *reinterpret_cast<unsigned*>(dst + (size_t)img * dst_stride + (size_t)y * dst_pitch + x4) = out;
+        }
+        return;
+    }
+    // gather path; images in groups of JSFE_REMAP_UNROLL: all 16 x U tap loads are issued before the first is used
     for (int img0 = blockIdx.z * JSFE_REMAP_UNROLL; img0 < n_images; img0 += gridDim.z * JSFE_REMAP_UNROLL) {
         int v[JSFE_REMAP_UNROLL][4][4];
 #pragma unroll

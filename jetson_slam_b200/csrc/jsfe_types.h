@@ -29,9 +29,6 @@ struct LevelGeom {
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
     unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
     uint8_t* img;                    // level image of slot 0
-    uint8_t* amb;                    // k_blur -> k_blur_fix: 4-bit ambiguity mask per 4-pixel group of the blurred interior
-    int amb_pitch;                   // bytes per mask row (multiple of 16)
-    unsigned long long amb_stride;   // bytes between slots
     uint8_t* blur;                   // 7x7-blurred level image of slot 0 (same pitch/stride; zero outside [B,h-B)x[B,w-B))
     const uint8_t* mask;             // [h][pitch] or nullptr (all pass); shared by all slots
 };
@@ -88,9 +85,7 @@ struct Params {
     int ms_table_size;                                // power of two >= 2*cap
     int *ms_keys, *ms_sums, *ms_cnts;                 // [slot][ms_table_size]
     uint8_t* ms_drop;                                 // [slot][cap]
-    unsigned blur_amb_units;                          // JSFE_BLUR_AMB_UNITS (3 x 2^-12); see DESIGN.md 4.2
-    int fix_items_total;                              // k_blur_fix threads (16 mask bytes each) over all levels
-    int fix_item_start[JSFE_MAXL + 1];
+    unsigned blur_amb_units;                          // JSFE_BLUR_AMB_UNITS (18 x 2^-15); see DESIGN.md 4.2
 };
 
 // TMA descriptors (cuTensorMapEncodeTiled, 3-D u8 tensors {pitch, h, slots}), passed as one __grid_constant__ parameter.

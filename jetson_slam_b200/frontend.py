@@ -82,6 +82,7 @@ def lib():
                                        C.POINTER(C.c_int64)]
         L.jsfe_pack_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_get_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
+        L.jsfe_pack_keypoints_once.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
         L.jsfe_process_host_pairs.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(HostResults)]
@@ -272,7 +273,7 @@ class Frontend:
         _check(lib().jsfe_slot_view_get(self._h, slot, C.byref(v)))
         return v
 
-    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms", "k_blur", "k_blur_fix")
+    STAGES = ("k_pyramid", "k_fast_cells", "k_compact", "k_orient_desc", "k_stereo_match", "k_stereo_outlier", "k_nms_ms", "k_blur")
 
     def profile(self, on=True):
         _check(lib().jsfe_profile_enable(self._h, int(on)))

@@ -1,6 +1,6 @@
 // sbp_driver.cpp -- builds a Frame pair from plain arrays, runs the REFERENCE's own host code of
 // ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) on it and hands the outcome back through a C entry point.
-// TEST INFRASTRUCTURE (oracle/): produces the fixtures tests/golden/ref_sbp_*.npz (tools/make_golden_sbp.py).
+// TEST INFRASTRUCTURE (oracle/): produces the fixtures tests/golden/sbpref_*.npz (tools/make_golden_sbp.py).
 // The function bodies are NOT in this repository: extract_slice.py cuts them out of the reference checkout by line range at
 // build time (oracle/_ref/gen/*.inc); this file only supplies what surrounds them.
 #include "sbp_stub.hpp"

@@ -187,7 +187,7 @@ def test_degenerate_inputs_match_reference_golden():
 
 def test_blur_is_exact_on_flat_and_saturated_images():
     """Constant / two-level / saturated windows put the separable blur value within 1e-5 of an integer, i.e. they all
-    take the exact-chain fallback (k_blur_fix); the stored bytes must still be the reference's."""
+    take the exact-chain fallback (the list pass at the end of k_blur); the stored bytes must still be the reference's."""
     cfg = CONFIGS["C1"]
     rng = np.random.default_rng(3)
     imgs = dict(synth.degenerate_images(cfg.height, cfg.width))

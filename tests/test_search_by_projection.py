@@ -1,6 +1,6 @@
 """ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) fused on the device.
 
-Pin      : tests/golden/ref_sbp_*.npz are outputs of the REFERENCE'S OWN host code -- src/ORBmatcher.cpp:1647-1963 and :2097-2138,
+Pin      : tests/golden/sbpref_*.npz are outputs of the REFERENCE'S OWN host code -- src/ORBmatcher.cpp:1647-1963 and :2097-2138,
            src/Frame.cpp:464-479, 569-639 and 696-706, cut out of the reference checkout by line range at build time and compiled
            unmodified against minimal Frame / MapPoint / cv::Mat stand-ins (oracle/ref_build/sbp_slice/, `make -C oracle/ref_build
            sbp`); its two device calls run the oracle's restatements of those kernels, which are pinned against the reference's
@@ -148,7 +148,7 @@ def assert_same(a, b):
 def _fixture(name):
     import os
     from conftest import ROOT
-    g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_sbp_{name}.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"sbpref_{name}.npz"))
     c = sbp_cases.build(name)
     assert int(g["input_checksum"]) == sbp_cases.checksum(c), "the seeded inputs changed: regenerate with tools/make_golden_sbp.py"
     assert int(g["level_mode"]) == c["expect_mode"], "bForward / bBackward of the reference's pose test"
