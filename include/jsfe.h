@@ -200,6 +200,25 @@ int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, co
                     int max_x, int min_y, int max_y, int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz,
                     float* u, float* v, int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream);
 
+/* ---- SURVEY.md 8(f2), the resident form: Tracking::SearchLocalPoints re-packs nine float arrays of every local map point and uploads
+ * them for EVERY frame (src/Tracking.cpp:1486-1561) although map points change far less often than frames arrive.  A jsfe_mappool
+ * keeps that SoA on the device under stable slot ids (e.g. MapPoint::mnId modulo the capacity, or an index the caller maintains):
+ *   jsfe_mappool_update     uploads n new / moved map points (HOST arrays, what GetWorldPosNormalExp and GetDistanceInvariances return)
+ *                           into slots ids[i]: called when LocalMapping changes them;
+ *   jsfe_mappool_in_frustum compute_isInFrustum_GPU (include/cuda/tracking_gpu.hpp:13-28) for the n pool points `ids_dev` (DEVICE int32
+ *                           list) under the HOST pose: per frame 4 bytes per point and 15 floats cross PCIe instead of 36 bytes per point.
+ * Outputs are DEVICE arrays indexed by the position in ids_dev, identical to jsfe_in_frustum on the gathered arrays. */
+typedef struct jsfe_mappool jsfe_mappool;
+int jsfe_mappool_create(int capacity, int device_id, jsfe_mappool** out);
+int jsfe_mappool_destroy(jsfe_mappool* p);
+int jsfe_mappool_update(jsfe_mappool* p, int n, const int32_t* ids, const float* px, const float* py, const float* pz, const float* pnx,
+                        const float* pny, const float* pnz, const float* max_distance, const float* invariance_max_distance,
+                        const float* invariance_min_distance, void* stream);
+int jsfe_mappool_in_frustum(jsfe_mappool* p, int n, const int32_t* ids_dev, const float* rcw9_host, const float* tcw3_host,
+                            const float* ow3_host, float fx, float fy, float cx, float cy, int min_x, int max_x, int min_y, int max_y,
+                            int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz, float* u, float* v,
+                            int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream);
+
 /* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) as ONE device
  * pass (replaces the live branch src/ORBmatcher.cpp:1647-1963: 2 kernels + 3 host loops + 9 copies per call).
  * All pointers are DEVICE pointers; work is enqueued on `stream`, not synchronised.

@@ -1114,12 +1114,14 @@ int jsfe_in_frustum(int n, const float* px, const float* py, const float* pz, co
                     const float* rcw9, const float* tcw3, const float* ow3, float fx, float fy, float cx, float cy, int min_x,
                     int max_x, int min_y, int max_y, int n_scale_levels, float log_scale_factor, float view_cos_angle, float* invz,
                     float* u, float* v, int32_t* predicted_level, float* view_cos, uint8_t* is_infrustum, void* stream) {
-    if (n < 0) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n < 0 || (n && (!px || !py || !pz || !pnx || !pny || !pnz || !max_distance || !invariance_max_distance || !invariance_min_distance || !rcw9 ||
+                        !tcw3 || !ow3 || !invz || !u || !v || !predicted_level || !view_cos || !is_infrustum)))
+        return fail(JSFE_ERR_INVALID, "bad argument");
     if (n == 0) return JSFE_OK;
     jsfe::k_in_frustum<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, px, py, pz, pnx, pny, pnz, max_distance, invariance_max_distance,
                                                                             invariance_min_distance, rcw9, tcw3, ow3, fx, fy, cx, cy, min_x, max_x,
                                                                             min_y, max_y, n_scale_levels, log_scale_factor, view_cos_angle, invz, u, v,
-                                                                            predicted_level, view_cos, is_infrustum);
+                                                                            predicted_level, view_cos, is_infrustum, nullptr);
     CU(cudaGetLastError());
     return JSFE_OK;
 }
@@ -1462,6 +1464,102 @@ int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out) {
 int jsfe_gather_set_peers_mapped(jsfe_gather* g, int all_mapped) {
     if (!g) return fail(JSFE_ERR_INVALID, "null gather");
     g->peer_all_mapped = all_mapped != 0;
+    return JSFE_OK;
+}
+
+
+// ================================================================================================= SURVEY.md 8(f2): resident map points
+// Tracking::SearchLocalPoints (src/Tracking.cpp:1346-1806) re-packs nine float arrays of every local map point on the host and
+// uploads them for each frame; map points change far less often than frames arrive.  The pool keeps that SoA on the device under
+// stable slot ids: a frame sends its list of ids (4 bytes per point instead of 36) and the pose.
+struct jsfe_mappool {
+    int device = 0, capacity = 0;
+    float* soa = nullptr;        // [9][capacity]: x y z | nx ny nz | max_distance | invariance_max | invariance_min
+    float* stage = nullptr;      // device staging of an update: [9][capacity]
+    int32_t* stage_ids = nullptr;
+    float* h_stage = nullptr;    // pinned mirror of the staging area
+    int32_t* h_ids = nullptr;
+    float* pose = nullptr;       // 15 floats on the device: Rcw (9) | tcw (3) | Ow (3)
+    float* h_pose = nullptr;
+};
+
+int jsfe_mappool_destroy(jsfe_mappool* p) {
+    if (!p) return JSFE_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (p->soa) cudaFree(p->soa);
+    if (p->stage) cudaFree(p->stage);
+    if (p->stage_ids) cudaFree(p->stage_ids);
+    if (p->pose) cudaFree(p->pose);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    if (p->h_ids) cudaFreeHost(p->h_ids);
+    if (p->h_pose) cudaFreeHost(p->h_pose);
+    delete p;
+    return JSFE_OK;
+}
+
+int jsfe_mappool_create(int capacity, int device_id, jsfe_mappool** out) {
+    if (!out || capacity < 1) return fail(JSFE_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    CU(cudaSetDevice(device_id));
+    jsfe_mappool* p = new (std::nothrow) jsfe_mappool;
+    if (!p) return fail(JSFE_ERR_INVALID, "out of host memory");
+    p->device = device_id; p->capacity = capacity;
+    const size_t n9 = (size_t)9 * capacity * sizeof(float);
+    cudaError_t e = cudaMalloc((void**)&p->soa, n9);
+    if (e == cudaSuccess) e = cudaMemset(p->soa, 0, n9);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->stage, n9);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->stage_ids, (size_t)capacity * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pose, 15 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_stage, n9);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ids, (size_t)capacity * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_pose, 15 * sizeof(float));
+    if (e != cudaSuccess) { jsfe_mappool_destroy(p); return fail(JSFE_ERR_CUDA, "map pool allocation failed: %s", cudaGetErrorString(e)); }
+    *out = p;
+    return JSFE_OK;
+}
+
+int jsfe_mappool_update(jsfe_mappool* p, int n, const int32_t* ids, const float* px, const float* py, const float* pz, const float* pnx,
+                        const float* pny, const float* pnz, const float* max_distance, const float* invariance_max_distance,
+                        const float* invariance_min_distance, void* stream) {
+    if (!p || n < 0 || n > p->capacity || (n && (!ids || !px || !py || !pz || !pnx || !pny || !pnz || !max_distance || !invariance_max_distance || !invariance_min_distance)))
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n == 0) return JSFE_OK;
+    for (int i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= p->capacity) return fail(JSFE_ERR_CAPACITY, "map point id %d outside the pool of %d", ids[i], p->capacity);
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaStreamSynchronize(st));     // the pinned staging area is reused from call to call
+    const float* src[9] = {px, py, pz, pnx, pny, pnz, max_distance, invariance_max_distance, invariance_min_distance};
+    for (int a = 0; a < 9; ++a) memcpy(p->h_stage + (size_t)a * n, src[a], (size_t)n * sizeof(float));
+    memcpy(p->h_ids, ids, (size_t)n * 4);
+    CU(cudaMemcpyAsync(p->stage, p->h_stage, (size_t)9 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p->stage_ids, p->h_ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    jsfe::k_mappool_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, p->stage_ids, p->stage, n, p->soa, p->capacity);
+    CU(cudaGetLastError());
+    return JSFE_OK;
+}
+
+int jsfe_mappool_in_frustum(jsfe_mappool* p, int n, const int32_t* ids_dev, const float* rcw9_host, const float* tcw3_host, const float* ow3_host,
+                            float fx, float fy, float cx, float cy, int min_x, int max_x, int min_y, int max_y, int n_scale_levels,
+                            float log_scale_factor, float view_cos_angle, float* invz, float* u, float* v, int32_t* predicted_level,
+                            float* view_cos, uint8_t* is_infrustum, void* stream) {
+    if (!p || n < 0 || n > p->capacity || (n && (!ids_dev || !rcw9_host || !tcw3_host || !ow3_host || !invz || !u || !v || !predicted_level || !view_cos || !is_infrustum)))
+        return fail(JSFE_ERR_INVALID, "bad argument");
+    if (n == 0) return JSFE_OK;
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaStreamSynchronize(st));     // the pinned pose block is reused from call to call
+    memcpy(p->h_pose, rcw9_host, 9 * sizeof(float));
+    memcpy(p->h_pose + 9, tcw3_host, 3 * sizeof(float));
+    memcpy(p->h_pose + 12, ow3_host, 3 * sizeof(float));
+    CU(cudaMemcpyAsync(p->pose, p->h_pose, 15 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const size_t c = (size_t)p->capacity;
+    const float* a = p->soa;
+    jsfe::k_in_frustum<<<(n + 255) / 256, 256, 0, st>>>(n, a, a + c, a + 2 * c, a + 3 * c, a + 4 * c, a + 5 * c, a + 6 * c, a + 7 * c, a + 8 * c, p->pose,
+                                                         p->pose + 9, p->pose + 12, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_scale_levels,
+                                                         log_scale_factor, view_cos_angle, invz, u, v, predicted_level, view_cos, is_infrustum, ids_dev);
+    CU(cudaGetLastError());
     return JSFE_OK;
 }
 

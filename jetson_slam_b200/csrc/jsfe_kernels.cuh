@@ -1648,11 +1648,13 @@ __global__ void __launch_bounds__(256) k_in_frustum(int n, const float* __restri
                                                     float cx, float cy, int min_x, int max_x, int min_y, int max_y, int n_levels,
                                                     float log_sf, float view_cos_angle, float* __restrict__ invz, float* __restrict__ u,
                                                     float* __restrict__ v, int* __restrict__ level, float* __restrict__ view_cos,
-                                                    uint8_t* __restrict__ in) {
+                                                    uint8_t* __restrict__ in, const int* __restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t ok = 0;
-    const float x = px[i], y = py[i], z = pz[i];
+    // ids != nullptr: query i is map point ids[i] of a RESIDENT pool (jsfe_mappool_*); the outputs stay indexed by the query
+    const int s = ids ? ids[i] : i;
+    const float x = px[s], y = py[s], z = pz[s];
     const float X = dot3_plus(x, __ldg(Rcw + 0), y, __ldg(Rcw + 1), z, __ldg(Rcw + 2), __ldg(tcw + 0));
     const float Y = dot3_plus(x, __ldg(Rcw + 3), y, __ldg(Rcw + 4), z, __ldg(Rcw + 5), __ldg(tcw + 1));
     const float Z = dot3_plus(x, __ldg(Rcw + 6), y, __ldg(Rcw + 7), z, __ldg(Rcw + 8), __ldg(tcw + 2));
@@ -1663,10 +1665,10 @@ __global__ void __launch_bounds__(256) k_in_frustum(int n, const float* __restri
             const float ox = __fsub_rn(x, __ldg(Ow + 0)), oy = __fsub_rn(y, __ldg(Ow + 1)), oz = __fsub_rn(z, __ldg(Ow + 2));
             // association measured on the reference's sm_100a build: the SECOND product is the plain FMUL (tests/test_helpers.py)
             const float dist = __fsqrt_rn(__fmaf_rn(oz, oz, __fmaf_rn(ox, ox, __fmul_rn(oy, oy))));
-            if (!(dist < inv_min[i] || dist > inv_max[i])) {
-                const float vc = __fdiv_rn(__fmaf_rn(oz, pnz[i], __fmaf_rn(ox, pnx[i], __fmul_rn(oy, pny[i]))), dist);
+            if (!(dist < inv_min[s] || dist > inv_max[s])) {
+                const float vc = __fdiv_rn(__fmaf_rn(oz, pnz[s], __fmaf_rn(ox, pnx[s], __fmul_rn(oy, pny[s]))), dist);
                 if (!(vc < view_cos_angle)) {
-                    const float ratio = __fdiv_rn(max_distance[i], dist);
+                    const float ratio = __fdiv_rn(max_distance[s], dist);
                     int ns = (int)ceilf(__fdiv_rn(logf(ratio), log_sf));
                     if (ns < 0) ns = 0; else if (ns >= n_levels) ns = n_levels - 1;
                     u[i] = uu; v[i] = vv; invz[i] = iz; level[i] = ns; view_cos[i] = vc;
@@ -1676,6 +1678,16 @@ __global__ void __launch_bounds__(256) k_in_frustum(int n, const float* __restri
         }
     }
     in[i] = ok;
+}
+
+// jsfe_mappool_update: scatter n refreshed map points (staged contiguously) to their slots of the resident SoA
+__global__ void __launch_bounds__(256) k_mappool_scatter(int n, const int* __restrict__ ids, const float* __restrict__ staged, int stage_stride,
+                                                         float* __restrict__ pool, int pool_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = ids[i];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) pool[(size_t)a * pool_stride + s] = staged[(size_t)a * stage_stride + i];
 }
 
 }  // namespace jsfe

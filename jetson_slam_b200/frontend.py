@@ -106,6 +106,10 @@ def lib():
         L.jsfe_profile_read.argtypes = [vp, vp, vp, C.c_int]
         L.jsfe_launch_count.restype = C.c_int64
         L.jsfe_launch_count.argtypes = [vp]
+        L.jsfe_mappool_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+        L.jsfe_mappool_destroy.argtypes = [vp]
+        L.jsfe_mappool_update.argtypes = [vp, C.c_int] + [vp] * 10 + [vp]
+        L.jsfe_mappool_in_frustum.argtypes = [vp, C.c_int, vp, vp, vp, vp] + [f] * 4 + [C.c_int] * 5 + [f] * 2 + [vp] * 6 + [vp]
         L.jsfe_gather_region_bytes.restype = C.c_int64
         L.jsfe_gather_region_bytes.argtypes = [vp, C.c_int]
         L.jsfe_gather_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -402,6 +406,51 @@ def in_frustum(P, Pn, max_distance, inv_max, inv_min, Rcw, tcw, Ow, fx, fy, cx, 
                                  max_y, n_levels, log_scale_factor, view_cos_angle, _ptr(iz), _ptr(u), _ptr(v), _ptr(lvl), _ptr(vc),
                                  _ptr(ok), _stream_ptr(stream)))
     return iz, u, v, lvl, vc, ok
+
+
+class MapPool:
+    """Resident map-point SoA (jsfe_mappool_*): update() when map points change, in_frustum() per frame with a device id list."""
+
+    def __init__(self, capacity, device=0):
+        self._p = C.c_void_p()
+        self.capacity, self.device = capacity, device
+        _check(lib().jsfe_mappool_create(capacity, device, C.byref(self._p)))
+
+    def update(self, ids, P, Pn, max_distance, inv_max, inv_min, stream=None):
+        """Host arrays: ids int32 [n]; P, Pn float32 [3, n]; the three distance arrays float32 [n]."""
+        a = lambda v, t: np.ascontiguousarray(v, t)
+        ids, P, Pn = a(ids, np.int32), a(P, np.float32), a(Pn, np.float32)
+        md, ima, imi = a(max_distance, np.float32), a(inv_max, np.float32), a(inv_min, np.float32)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        _check(lib().jsfe_mappool_update(self._p, len(ids), p(ids), p(P[0]), p(P[1]), p(P[2]), p(Pn[0]), p(Pn[1]), p(Pn[2]), p(md), p(ima), p(imi),
+                                         _stream_ptr(stream)))
+
+    def in_frustum(self, ids_dev, Rcw, tcw, Ow, fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels, log_scale_factor, view_cos_angle, stream=None):
+        """ids_dev: int32 CUDA tensor; Rcw [9], tcw [3], Ow [3]: host float32.  Returns the same tuple as in_frustum()."""
+        import torch
+        n = ids_dev.shape[0]
+        dev = ids_dev.device
+        iz, u, v, vc = (torch.zeros(n, dtype=torch.float32, device=dev) for _ in range(4))
+        lvl = torch.zeros(n, dtype=torch.int32, device=dev)
+        ok = torch.empty(n, dtype=torch.uint8, device=dev)
+        a = lambda x: np.ascontiguousarray(x, np.float32)
+        R, t, O = a(Rcw), a(tcw), a(Ow)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        _check(lib().jsfe_mappool_in_frustum(self._p, n, _ptr(ids_dev), p(R), p(t), p(O), fx, fy, cx, cy, min_x, max_x, min_y, max_y, n_levels,
+                                             log_scale_factor, view_cos_angle, _ptr(iz), _ptr(u), _ptr(v), _ptr(lvl), _ptr(vc), _ptr(ok),
+                                             _stream_ptr(stream)))
+        return iz, u, v, lvl, vc, ok
+
+    def close(self):
+        if self._p:
+            lib().jsfe_mappool_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------------- SURVEY 8(f1)

@@ -110,3 +110,37 @@ def test_helpers_match_oracle_and_reference_kernels():
         L.jsref_hamming_pairs(50000, p(t_il), p(t_ir), p(t_dl), p(t_dr), p(d2))
         torch.cuda.synchronize()
         assert np.array_equal(d2.cpu().numpy(), d)
+
+
+@pytest.mark.gpu
+def test_resident_map_pool_equals_the_stateless_frustum_kernel():
+    """the map-point SoA stays on the device (jsfe_mappool_*); a frame sends ids + pose.  Must equal jsfe_in_frustum /
+    the oracle on the gathered arrays, before and after some map points move."""
+    import torch
+    from jetson_slam_b200 import frontend
+    dev = torch.device("cuda", 0)
+    N = 30000
+    P, Pn, R, t, Ow, maxd, ima, imi = _scene(N, 11)
+    pool = frontend.MapPool(N + 100)
+    slots = np.random.default_rng(2).permutation(N + 100)[:N].astype(np.int32)     # map point k lives in slot slots[k]
+    pool.update(slots, P, Pn, maxd, ima, imi)
+    fr = dict(min_x=0, max_x=1241, min_y=0, max_y=376, n_levels=8, log_scale_factor=float(np.log(np.float32(1.2))), view_cos_angle=0.5)
+
+    def check(query, Pq, Pnq, mdq, imaq, imiq):
+        got = [x.cpu().numpy() for x in pool.in_frustum(torch.from_numpy(slots[query]).to(dev), R, t, Ow, **K, **fr)]
+        want = orc.in_frustum(Pq, Pnq, mdq, imaq, imiq, R, t, Ow, **K, **fr)
+        m = want[5] == 1
+        assert np.array_equal(got[5], want[5]) and m.sum() > 50
+        for g, w in zip(got[:5], want[:5]):
+            assert np.array_equal(g[m].view(np.uint8), w[m].view(np.uint8))
+
+    q = np.random.default_rng(3).permutation(N)[:12000]          # this frame's local map: a subset, in any order
+    check(q, np.ascontiguousarray(P[:, q]), np.ascontiguousarray(Pn[:, q]), maxd[q], ima[q], imi[q])
+    moved = q[:500]                                                # LocalMapping moves some points
+    P2 = P.copy()
+    P2[:, moved] += np.float32(0.25)
+    pool.update(slots[moved], np.ascontiguousarray(P2[:, moved]), np.ascontiguousarray(Pn[:, moved]), maxd[moved], ima[moved], imi[moved])
+    check(q, np.ascontiguousarray(P2[:, q]), np.ascontiguousarray(Pn[:, q]), maxd[q], ima[q], imi[q])
+    with pytest.raises(frontend.JsfeError):
+        pool.update(np.array([N + 100], np.int32), P[:, :1], Pn[:, :1], maxd[:1], ima[:1], imi[:1])
+    pool.close()
