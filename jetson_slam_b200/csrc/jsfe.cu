@@ -258,8 +258,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         int T = (g.tile_h - 1) / n_loc + 1;
         if (T * 128 > 1024) T = 1024 / 128;
         g.T = T;
-        int fast_width = 192;   // pixels of cell group per k_fast_cells block (s_best and the colkey table hold 192 columns)
-        if (const char* e = getenv("JSFE_FAST_WIDTH")) fast_width = std::max(16, std::min(192, atoi(e)));
+        int fast_width = std::min(192, JSFE_FAST_PW - 32);   // pixels of cell group per k_fast_cells block (s_best and the colkey table hold 192 columns)
+        if (const char* e = getenv("JSFE_FAST_WIDTH")) fast_width = std::max(16, std::min(fast_width, atoi(e)));
         g.cells_per_block = std::max(1, std::min(g.n_tile_w, fast_width / g.tile_w));
         g.blocks_per_row = (g.n_tile_w + g.cells_per_block - 1) / g.cells_per_block;
         g.block_offset = items;

@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
 //  dense, exact evaluation of the whole tile.
 // =================================================================================================
+#ifndef JSFE_FAST_PW
 #define JSFE_FAST_PW 224   // shared-memory pitch of the pixel tile = TMA box width: covers floor16 slack 15 + 4 + 192 + 4 (+ pad)
+#endif
 
 // per-byte MSB = (a > b), unsigned bytes; nb7 = ~b & 0x7f7f7f7f (hoisted when b is loop-invariant)
 __device__ __forceinline__ unsigned msb_gt(unsigned a, unsigned b, unsigned nb7) {
