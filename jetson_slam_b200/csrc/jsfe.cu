@@ -276,7 +276,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         g.fast_ngx_inv = 65536u / (unsigned)ngx + 1u;
         for (unsigned t = 0; t < 256; ++t)
             if (((t * g.fast_ngx_inv) >> 16) != t / (unsigned)ngx) { delete h; return fail(JSFE_ERR_INVALID, "internal: phase A reciprocal is not exact"); }
-        const size_t sw = (gw + 2 + 7) & ~(size_t)7;
+        const size_t sw = (size_t)jsfe::fast_score_pitch((int)gw);
         smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 2 + 64);  // pixels + scores + work list (the positives live in its gap)
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
         if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 31) / 32);

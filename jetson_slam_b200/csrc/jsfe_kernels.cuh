@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
 //  dense, exact evaluation of the whole tile.
 // =================================================================================================
+#ifndef JSFE_FAST_SWPAD
+#define JSFE_FAST_SWPAD 0     // extra u16 columns per score row: shifts the shared-memory banks from row to row
+#endif
+// score row length (u16) of a k_fast_cells block that owns gw columns
+__host__ __device__ __forceinline__ int fast_score_pitch(int gw) { return ((gw + 2 + 7) & ~7) + JSFE_FAST_SWPAD; }
 #ifndef JSFE_FAST_PW
 #define JSFE_FAST_PW 224   // shared-memory pitch of the pixel tile = TMA box width: covers floor16 slack 15 + 4 + 192 + 4 (+ pad)
 #endif
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int X0 = tx0 * lv.tile_w, GW = ncells * lv.tile_w, y0 = ty * lv.tile_h;
     const int gx0 = ((X0 - 4) >> 4) << 4, gy0 = y0 - 4;
     const int PR = lv.tile_h + 8;
-    const int SW = (GW + 2 + 7) & ~7;   // score row length (u16), multiple of 8 -> rows are 16-byte aligned
+    const int SW = fast_score_pitch(GW);   // score row length (u16)
     const int SR = lv.tile_h + 2;
     const int cs0 = X0 - 1 - gx0;       // tile column of score column 0
     uint8_t* pix = smem;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     }
     {
         uint4* z = reinterpret_cast<uint4*>(sc);
-        const int nz = (SR * SW) >> 3;
+        const int nz = (SR * SW + 7) >> 3;    // a ragged tail spills into the (still unused) work list
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < 192) s_best[tid] = 0;
         if (tid == 0) s_ncand = 0;
