@@ -138,6 +138,23 @@ def workload_config(cfg, pairs_per_gpu):
             "l2": "inputs>L2 (%.0f MB of level-0 images per step per GPU)" % (2 * pairs_per_gpu * cfg.height * cfg.width / 1e6)}
 
 
+_FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None   # before any NUMA pinning
+
+
+class full_affinity:
+    """The CPU legs run on every host core the process started with, not on the NUMA node the GPU arm pinned itself to, so both
+    arms search and use the same thread counts."""
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0) if _FULL_AFFINITY is not None else None
+        if _FULL_AFFINITY is not None:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+
+
 def pin_to_gpu_numa(index):
     """Bind this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned buffers are allocated (first touch): on the
     8-GPU box ranks 0-3 sit on node 0 and 4-7 on node 1, and unpinned uploads from the wrong socket cost ~5 % at N = 8."""
@@ -774,9 +791,10 @@ def run_ours(args, cfg):
     if rank == 0:
         if lat is not None and world == 1:
             lat["device_resident_ladder"] = device_ladder()
-        cpu_threads, cpu_tried = best_cpu_threads(cfg, pairs[: min(4, len(pairs))], args.cpu_threads)
-        sample_pairs = 6 * cpu_threads   # ~15 s of CPU work
-        cpu_v, cpu_dt = cpu_pairs_per_s(cfg, pairs[: min(4, len(pairs))], cpu_threads, sample_pairs)
+        with full_affinity():
+            cpu_threads, cpu_tried = best_cpu_threads(cfg, pairs[: min(4, len(pairs))], args.cpu_threads)
+            sample_pairs = 20 * cpu_threads   # a bounded sample of the same workload: ~20 s of CPU work
+            cpu_v, cpu_dt = cpu_pairs_per_s(cfg, pairs[: min(4, len(pairs))], cpu_threads, sample_pairs)
         config = workload_config(cfg, B)
         config["parallelism"] = f"pairs sharded one-batch-per-GPU x{world}, no data-path collective in `value`" + ("; `gather` adds the exchange step" if gather_info else "")
         line = {

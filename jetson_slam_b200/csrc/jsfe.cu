@@ -223,6 +223,8 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     }
     int cells = 0, tile_rows = 0, items = 0;
     size_t smem_max = 0;
+    int debug_cap = 0;
+    if (const char* e = getenv("JSFE_DEBUG_FAST_CAP")) debug_cap = std::max(0, atoi(e));   // tests: force the work-list overflow path
     P.pyr_block_start[0] = 0;
     P.pyr_block_start[1] = 0;
     for (int i = 0; i < P.L; ++i) {
@@ -258,7 +260,13 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         int T = (g.tile_h - 1) / n_loc + 1;
         if (T * 128 > 1024) T = 1024 / 128;
         g.T = T;
-        int fast_width = std::min(192, JSFE_FAST_PW - 32);   // pixels of cell group per k_fast_cells block (s_best and the colkey table hold 192 columns)
+#ifndef JSFE_FAST_BLOCKS
+#define JSFE_FAST_BLOCKS 6    // k_fast_cells blocks per SM the shared-memory budget aims at (6 x 256 threads x 40 registers fit)
+#endif
+#ifndef JSFE_FAST_GW
+#define JSFE_FAST_GW 192      // widest cell group of a k_fast_cells block (A/B knob; s_best and the colkey table hold 192 columns)
+#endif
+        int fast_width = std::min(std::min(192, JSFE_FAST_GW), JSFE_FAST_PW - 23);   // pixels of cell group per k_fast_cells block (s_best and the colkey table hold 192 columns)
         if (const char* e = getenv("JSFE_FAST_WIDTH")) fast_width = std::max(16, std::min(fast_width, atoi(e)));
         g.cells_per_block = std::max(1, std::min(g.n_tile_w, fast_width / g.tile_w));
         g.blocks_per_row = (g.n_tile_w + g.cells_per_block - 1) / g.cells_per_block;
@@ -268,7 +276,7 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         const size_t pw = JSFE_FAST_PW, pr = g.tile_h + 8;   // fixed pitch: covers X0+GW+4-gx0 (<= 19 + 192 + 4) with gx0 = floor16(X0-4)
         if (gw + 8 + 15 > pw) { delete h; return fail(JSFE_ERR_INVALID, "internal: cell group wider than the staged tile"); }
         g.tile_pw = (int)pw;
-        // phase A thread grid: 8-pixel column groups covering score columns [cs0-0, cs0+gw+1], cs0 = X0-1-floor16(X0-4) in [3,18]
+        // phase A thread grid: 8-pixel column groups covering score columns [cs0, cs0+gw+1], cs0 = X0-1-floor16(X0-4) in [3,18]
         int ngx = 1;
         for (int cs0 = 3; cs0 <= 18; ++cs0) ngx = std::max(ngx, (int)((cs0 + gw + 1) >> 3) - (cs0 >> 3) + 1);
         g.fast_ngx = ngx;
@@ -276,8 +284,18 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
         g.fast_ngx_inv = 65536u / (unsigned)ngx + 1u;
         for (unsigned t = 0; t < 256; ++t)
             if (((t * g.fast_ngx_inv) >> 16) != t / (unsigned)ngx) { delete h; return fail(JSFE_ERR_INVALID, "internal: phase A reciprocal is not exact"); }
+        // shared memory of a block: pixels + scores + work list.  The list gets what is left of the per-block budget that lets
+        // JSFE_FAST_BLOCKS blocks share an SM (228 KB, 1 KB reserved per block, ~1 KB static), at most one slot per score position;
+        // a tile with more survivors than slots is evaluated densely (exact, slower).  If the budget leaves less than a third of
+        // the positions, the list gets a third and fewer blocks fit.
         const size_t sw = (size_t)jsfe::fast_score_pitch((int)gw);
-        smem_max = std::max(smem_max, pr * pw + (size_t)(g.tile_h + 2) * sw * 2 * 2 + 64);  // pixels + scores + work list (the positives live in its gap)
+        const size_t positions = (size_t)(g.tile_h + 2) * sw, fixed = pr * pw + positions * 2 + 64;
+        const size_t budget = (228 * 1024) / JSFE_FAST_BLOCKS - 2048;
+        size_t cap = budget > fixed ? (budget - fixed) / 2 : 0;
+        cap = std::min(positions, std::max(cap, positions / 3));
+        if (debug_cap > 0) cap = std::min(cap, (size_t)debug_cap);
+        g.fast_cap = (int)cap;
+        smem_max = std::max(smem_max, fixed + cap * 2);
         g.slot_stride = align_up((size_t)g.h * g.pitch, 256);
         if (i >= 1) P.pyr_block_start[i + 1] = P.pyr_block_start[i] + ((g.pitch + 127) / 128) * ((g.h + 31) / 32);
         if (g.w >= 16384 || g.h >= 16384) { delete h; return fail(JSFE_ERR_INVALID, "images larger than 16383 pixels are not supported"); }
@@ -375,8 +393,6 @@ int jsfe_create(const jsfe_config* cfg, jsfe_handle** out) {
     }
     P.fast_q_thresh = P.threshold >= 3 ? (P.threshold - 3) / 4 + 1 : 0;
     if (P.threshold < 0 || P.threshold > 255) { delete T; delete h; return fail(JSFE_ERR_INVALID, "th_fast_max must be in [0,255]"); }
-    P.fast_list_cap = 0;
-    if (const char* e = getenv("JSFE_DEBUG_FAST_CAP")) P.fast_list_cap = std::max(0, atoi(e));   // tests: force the overflow paths
     for (int m = 0; m < 0x10000; ++m) {   // LUT in the bit order k_fast_cells' flag merge produces (see fast_eval)
         if (!((T->lut_bits[m >> 5] >> (m & 31)) & 1u)) continue;
         unsigned idx = 0;

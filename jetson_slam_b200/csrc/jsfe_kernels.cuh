@@ -171,11 +171,14 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
 //  dense, exact evaluation of the whole tile.
 // =================================================================================================
+#ifndef JSFE_EMIT
+#define JSFE_EMIT 0           // emission loop variant (A/B knob)
+#endif
 #ifndef JSFE_FAST_SWPAD
 #define JSFE_FAST_SWPAD 0     // extra u16 columns per score row: shifts the shared-memory banks from row to row
 #endif
 // score row length (u16) of a k_fast_cells block that owns gw columns
-__host__ __device__ __forceinline__ int fast_score_pitch(int gw) { return ((gw + 2 + 7) & ~7) + JSFE_FAST_SWPAD; }
+__host__ __device__ __forceinline__ int fast_score_pitch(int gw) { return ((gw + 2 + 1) & ~1) + JSFE_FAST_SWPAD; }
 #ifndef JSFE_FAST_PW
 #define JSFE_FAST_PW 224   // shared-memory pitch of the pixel tile = TMA box width: covers floor16 slack 15 + 4 + 192 + 4 (+ pad)
 #endif
@@ -272,8 +275,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     __shared__ unsigned s_best[192];
     __shared__ uint16_t s_codeoff[32];   // emission: code offset of accumulator bit b = (b & 7) * (nrl << 8) + (b >> 3)
     __shared__ unsigned s_ncand;      // work-list counters, packed: bright | dark << 16
-    __shared__ __align__(16) int s_npos[8];   // positives per warp (each warp owns an eighth of the positives area: no atomics, and
-                                              // phase C walks a warp's own segment); -1 = that segment overflowed
+    __shared__ int s_npos[8];         // positives per warp (phase C walks a warp's own positives)
     constexpr int PW = JSFE_FAST_PW;
     pdl_launch_dependents();
     const uint32_t item = __ldg(p.fast_map + blockIdx.x);   // level << 28 | tile row << 14 | block in row
@@ -291,11 +293,11 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     const int cs0 = X0 - 1 - gx0;       // tile column of score column 0
     uint8_t* pix = smem;
     uint16_t* sc = reinterpret_cast<uint16_t*>(smem + (size_t)PR * PW);
-    // work list of codes (score row << 8 | score column), one slot per score position: bright survivors from the front, dark ones
-    // from the back (a position can be in both); the gap in between later holds the positives.  cap < capf only in overflow tests.
+    // work list of codes (score row << 8 | score column), lv.fast_cap slots (the host sizes it so that the wanted number of blocks
+    // fits an SM; tiles with more survivors take the dense fallback): bright survivors from the front, dark ones from the back.
+    // Phase B later overwrites entries it has consumed with the positives.
     uint16_t* cand = sc + (size_t)SR * SW;
-    const int capf = SR * SW;
-    const int cap = p.fast_list_cap > 0 ? min(p.fast_list_cap, capf) : capf;
+    const int cap = lv.fast_cap;
     const uint8_t* __restrict__ img = lv.img + (size_t)slot * lv.slot_stride;
     const int tid = threadIdx.x, lane = tid & 31;
     // pixels whose score can be non-zero: interior [B, w-B) x [B, h-B) (score positions of this block: rows ry, columns rx)
@@ -416,11 +418,15 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 int ob = (int)((base & 0xffffu) + (incl & 0xffffu)) - cb;     // first bright slot of this thread
                 int od = (int)((base >> 16) + (incl >> 16)) - cd;            // first dark slot (counted from the back)
                 const int code_base = code_first - (8 - nit) * cstep;
-                // one entry per set bit, highest first; slots stay inside the list (at most one entry per position and polarity)
+                // one entry per set bit, highest first
                 uint16_t* pb = cand + ob;                 // bright: upwards from the front
-                uint16_t* pd = cand + (capf - 1 - od);    // dark: downwards from the back
+                uint16_t* pd = cand + (cap - 1 - od);     // dark: downwards from the back
+                // a list that does not fit is never read (the counters still say so): keep the stores inside the array
+                if (ob + cb > cap) aba = abb = 0;
+                if (od + cd > cap) ada = adb = 0;
                 auto emit = [&](unsigned m, int col_off, uint16_t*& ptr, int dir) {
                     const int cb0 = code_base + col_off;
+#if JSFE_EMIT == 0
                     while (m) {
                         unsigned b;
                         asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));        // index of the highest set bit (FLO)
@@ -428,6 +434,19 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                         *ptr = (uint16_t)(cb0 + s_codeoff[b]);
                         ptr += dir;
                     }
+#else
+                    // lowest set bit first: the loop-carried chain is m &= m - 1 (two ALU ops), the bit index is off it
+                    while (m) {
+                        const unsigned b = (unsigned)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+#if JSFE_EMIT == 1
+                        *ptr = (uint16_t)(cb0 + (int)imad(b & 7u, (unsigned)cstep, b >> 3));
+#else
+                        *ptr = (uint16_t)(cb0 + s_codeoff[b]);
+#endif
+                        ptr += dir;
+                    }
+#endif
                 };
                 emit(aba, 0, pb, 1);
                 emit(abb, 4, pb, 1);
@@ -438,20 +457,20 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     }
     __syncthreads();
 
-    // ---- phase B: exact evaluation of the work list (one polarity per entry); hits store their score and join the positives.
-    //      The positives of warp w go to its eighth of the gap between the bright and the dark entries: positives <= entries
-    //      evaluated, so the gap cannot overflow while the work list is at most half full.
+    // ---- phase B: exact evaluation of the work list (one polarity per entry); hits store their score and become positives.
+    //      Warp w evaluates entries [256 it + 32 w, +32) in its it-th pass and writes its q-th positive over the (q & 31)-th entry of
+    //      its (q >> 5)-th pass: positives <= entries consumed, so they always fit, without atomics or a second array.
     const unsigned ncand2 = s_ncand;
     const int nb = (int)(ncand2 & 0xffffu), nd = (int)(ncand2 >> 16), ntot = nb + nd;
     const bool list_ok = ntot <= cap;
-    const int pos_seg = list_ok ? (p.fast_list_cap > 0 ? min(p.fast_list_cap, (capf - ntot) >> 3) : (capf - ntot) >> 3) : 0;
-    uint16_t* pos = cand + nb + (tid >> 5) * pos_seg;       // this warp's segment
+    auto slot_of = [&](int j) { return j < nb ? j : cap - 1 - (j - nb); };     // list index of the j-th entry
     {
         const uint32_t* __restrict__ lutp = p.tab->lut_perm;
         const uint8_t* cbase = pix + 3 * PW + cs0;
         if (list_ok) {
             const int nit = (ntot + 255) >> 8;        // warp-uniform trip count: the positives append is warp-collective
             const unsigned lt = (1u << lane) - 1u;
+            const int wbase = tid - lane;             // first entry of this warp in pass 0
             int wpos = 0;                              // positives of this warp so far (warp-uniform)
             for (int it = 0, i = tid; it < nit; ++it, i += 256) {
                 unsigned score = 0;
@@ -462,26 +481,27 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                     score = fast_eval<0>(cbase + (code >> 8) * PW + (code & 255), p.threshold, MODE, lutp);
                 } else if (w0 >= nb) {
                     if (i < ntot) {
-                        code = cand[capf - 1 - (i - nb)];
+                        code = cand[cap - 1 - (i - nb)];
                         score = fast_eval<1>(cbase + (code >> 8) * PW + (code & 255), p.threshold, MODE, lutp);
                     }
                 } else if (i < ntot) {
                     const bool dark = i >= nb;
-                    code = cand[dark ? capf - 1 - (i - nb) : i];
+                    code = cand[dark ? cap - 1 - (i - nb) : i];
                     const uint8_t* c = cbase + (code >> 8) * PW + (code & 255);
                     score = dark ? fast_eval<1>(c, p.threshold, MODE, lutp) : fast_eval<0>(c, p.threshold, MODE, lutp);
                 }
                 if (score) sc[(code >> 8) * SW + (code & 255)] = (uint16_t)score;
-                const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);
-                const int o = wpos + __popc(pb & lt);
-                if (score != 0u && o < pos_seg) pos[o] = (uint16_t)code;
+                const unsigned pb = __ballot_sync(0xffffffffu, score != 0u);   // every lane has read its entry by now
+                if (score != 0u) {
+                    const int q = wpos + __popc(pb & lt);
+                    cand[slot_of(((q >> 5) << 8) + wbase + (q & 31))] = (uint16_t)code;
+                }
                 wpos += __popc(pb);
             }
-            if (lane == 0) s_npos[tid >> 5] = wpos <= pos_seg ? wpos : -1;
+            if (lane == 0) s_npos[tid >> 5] = wpos;
         } else {
             // work list overflow (more survivors than score positions: adversarial input): every interior pixel, both polarities
             const int n = SR * SW;
-            if (lane == 0) s_npos[tid >> 5] = -1;
             for (int i = tid; i < n; i += 256) {
                 const int ry = i / SW, rx = i - ry * SW;
                 const int x = X0 - 1 + rx;
@@ -496,8 +516,8 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     }
     __syncthreads();
 
-    // ---- phase C: NMS + per-cell arg-max.  Every warp walks its own positives; if any segment overflowed (or the work list did),
-    //      the whole score tile is walked instead (exact, slower: noise-like or adversarial tiles only)
+    // ---- phase C: NMS + per-cell arg-max.  Every warp walks its own positives; if the work list overflowed, the whole score
+    //      tile is walked instead (exact, slower: noise-like or adversarial tiles only)
     {
         const int ymin = max(y0, JSFE_B), ymax = min(y0 + lv.tile_h, lv.h - JSFE_B);
         const int wv = min(GW, lv.w - X0);          // owned columns actually inside the image
@@ -515,12 +535,10 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 atomicMax(&s_best[ck & 0xFFu], key);
             }
         };
-        const int4 na = *reinterpret_cast<const int4*>(s_npos), nb4 = *reinterpret_cast<const int4*>(s_npos + 4);
-        const bool dense = (na.x | na.y | na.z | na.w | nb4.x | nb4.y | nb4.z | nb4.w) >= 0;
-        if (dense) {
+        if (list_ok) {
             const int npos = s_npos[tid >> 5];
-            for (int i = lane; i < npos; i += 32) {
-                const int code = pos[i];
+            for (int q = lane, j = tid; q < npos; q += 32, j += 256) {      // its q-th positive sits over its entry of pass q >> 5
+                const int code = cand[slot_of(j)];
                 const int ry = code >> 8, rx = code & 255;     // a positive: score > 0, row and column >= 1 by construction of phase A
                 nms(ry, rx, sc[ry * SW + rx]);
             }

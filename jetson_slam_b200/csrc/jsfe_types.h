@@ -26,6 +26,7 @@ struct LevelGeom {
     int block_offset;                // first k_fast_cells work item of this level
     int fast_ngx, fast_nrl;          // k_fast_cells phase A thread grid: 8-pixel column groups x row lanes (ngx*nrl <= 256)
     unsigned fast_ngx_inv;           // floor(65536/ngx)+1: tid/ngx == (tid*inv)>>16 for tid < 256
+    int fast_cap;                    // k_fast_cells work-list slots of a block of this level (<= score positions of the block)
     float scale, inv_scale, rscale;  // rscale = 1.0f / inv_scale (what the reference's resize kernel uses)
     unsigned long long slot_stride;  // bytes between consecutive slots of this level's image
     uint8_t* img;                    // level image of slot 0
@@ -60,7 +61,6 @@ struct Params {
     int use_tma;       // 1: tiles/windows are staged by TMA (cp.async.bulk.tensor), 0: by the threads (JSFE_NO_TMA=1)
     int compass_mode;  // k_fast_cells pre-test: adjacent compass points every accepted arc must cover (0..3)
     int fast_q_thresh; // k_fast_cells phase A: m = (t-3)/4 + 1 (0 for t < 3): p - v > t implies (p>>2) - (v>>2) >= m
-    int fast_list_cap; // 0 = work list holds every score position; > 0 (JSFE_DEBUG_FAST_CAP): forced small lists (overflow tests)
     int H0, W0;
     int pyr_blocks_total;             // k_pyramid blocks (128x32 pixel tiles) over levels 1..L-1
     int pyr_block_start[JSFE_MAXL + 1];
