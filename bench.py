@@ -490,8 +490,10 @@ def run_ours(args, cfg):
     # (it allocates and frees per frame, which gets slower the more the process has mapped)
     ref_cuda = ref_cuda_pairs_per_s(cfg, seeds[0]) if (rank == 0 and world == 1 and not args.no_ref_cuda) else None
     fe = frontend.Frontend(**cfg.extractor_kwargs(), device=local, max_images=2 * B)
-    host = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8).pin_memory()
-    hv = host.numpy()
+    # input images: pinned host memory from jsfe_host_alloc, write-combined unless --host-cached (the producer only writes it;
+    # uploads that are not snooped through the CPU caches are worth ~5 % of e2e once several GPUs of a socket upload at once)
+    host_buf = frontend.HostBuffer((2 * B, cfg.height, cfg.width), np.uint8, write_combined=not args.host_cached)
+    hv = host_buf.array
     for p in range(B):
         hv[2 * p], hv[2 * p + 1] = pairs[p % n_distinct]
     stream = torch.cuda.Stream()
@@ -617,16 +619,28 @@ def run_ours(args, cfg):
         parity["e2e_checked_pairs"], parity["e2e_mismatches"] = c2, b2
         parity["notes"] = (parity["notes"] + n2)[:8]
     # what the PCIe link alone gives for this step's input (pinned host -> device, nothing else running): the floor under e2e
-    dev_in = torch.empty_like(host, device="cuda")
+    dev_in = torch.empty((2 * B, cfg.height, cfg.width), dtype=torch.uint8, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dev_in.copy_(host, non_blocking=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(3):
-        dev_in.copy_(host, non_blocking=True)
-    ev1.record()
-    torch.cuda.synchronize()
-    h2d_ms = ev0.elapsed_time(ev1) / 3
+    try:
+        import ctypes as C
+        rt = C.CDLL("libcudart.so.12")     # the runtime torch has already loaded
+        rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    except OSError:
+        rt = None
+
+    def upload():
+        rt.cudaMemcpyAsync(dev_in.data_ptr(), hv.ctypes.data, hv.nbytes, 1, torch.cuda.current_stream().cuda_stream)
+
+    h2d_ms = None
+    if rt is not None:
+        upload()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(3):
+            upload()
+        ev1.record()
+        torch.cuda.synchronize()
+        h2d_ms = ev0.elapsed_time(ev1) / 3
     del dev_in
 
     # ---- N > 1: the same step with the results gathered on rank 0 (jsfe_gather_*), double-buffered over the two handles so that the
@@ -814,7 +828,8 @@ def run_ours(args, cfg):
                            "pinned host images in, pinned host result slabs out, wall clock over all steps",
                     "blocking_call": {"value": e2e_serial, "unit": UNIT, "ms_per_step": ms_e2e_serial / e2e_steps,
                                       "how": "one jsfe_process_host_pairs call per step (chunked 3-stream pipeline inside), nothing else in flight"},
-                    "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": 2 * B * cfg.height * cfg.width / h2d_ms / 1e6},
+                    "h2d_only_ms_per_step": h2d_ms, "h2d_only_gbs": 2 * B * cfg.height * cfg.width / h2d_ms / 1e6 if h2d_ms else None,
+                    "host_input": "jsfe_host_alloc, " + ("cached pinned" if args.host_cached else "write-combined pinned")},
             "gpu_launches": int(launches),
             "parity": parity,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -865,6 +880,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the gather measurements")
     ap.add_argument("--gather-transport", default="p2p", choices=["p2p", "nccl"], help="peer-memory stores over NVLink (CUDA IPC) or NCCL send/recv")
+    ap.add_argument("--host-cached", action="store_true", help="input images in ordinary (cached) pinned memory instead of write-combined")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against goldens and oracle")
     args = ap.parse_args()
     from jetson_slam_b200.configs import CONFIGS

@@ -183,6 +183,13 @@ int jsfe_process_host_pairs(jsfe_handle* h, int n_pairs, const uint8_t* images, 
 int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* images, int chunk_pairs, int th_high, int th_low,
                                   float mb, float mbf);
 int jsfe_process_host_pairs_end(jsfe_handle* h, jsfe_host_results* out);
+/* Pinned host memory for the `images` argument above (what SyncedMem's cudaMallocHost does in the reference,
+ * include/cuda/synced_mem_holder.hpp).  write_combined != 0 allocates it cudaHostAllocWriteCombined: the copy engine's reads are
+ * then not snooped through the CPU caches, which is worth ~5 % of host-to-host throughput once several GPUs of one socket upload
+ * at the same time (bench.py, 4 GPUs: 184 k -> 193 k pairs/s).  Write-combined memory is for buffers the host only WRITES
+ * (a capture / decode target); host reads of it are slow.  Free with jsfe_host_free. */
+int jsfe_host_alloc(void** ptr, size_t bytes, int write_combined);
+int jsfe_host_free(void* ptr);
 
 /* ---- adjacent rows: stateless helpers of the tracking thread.  All pointers are DEVICE pointers,
  * work is enqueued on `stream` and NOT synchronised (the compat shims synchronise, as the reference does).

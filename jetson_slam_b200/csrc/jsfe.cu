@@ -835,6 +835,24 @@ int jsfe_pack_keypoints(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t*
     return JSFE_OK;
 }
 
+int jsfe_host_alloc(void** ptr, size_t bytes, int write_combined) {
+    if (!ptr || bytes == 0) return fail(JSFE_ERR_INVALID, "jsfe_host_alloc: null pointer or zero size");
+    *ptr = nullptr;
+    if (cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JSFE_ERR_CUDA, "cudaHostAlloc(%zu bytes%s) failed", bytes, write_combined ? ", write-combined" : "");
+    }
+    return JSFE_OK;
+}
+
+int jsfe_host_free(void* ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(JSFE_ERR_CUDA, "cudaFreeHost failed");
+    }
+    return JSFE_OK;
+}
+
 int jsfe_pack_keypoints_once(jsfe_handle* h, int slot, int32_t* dst_kps_dev, uint8_t* dst_desc_dev, int32_t* n_out, void* stream) {
     int rc = check_slots(h, slot, 1);
     if (rc) return rc;

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
             acc = __fmaf_rn(__fmul_rn(wyt, wxl[k]), u8_to_f32(__ldg(r0 + xl[k])), acc);
             acc = __fmaf_rn(__fmul_rn(wyb, wxl[k]), u8_to_f32(__ldg(r1 + xl[k])), acc);
             acc = __fmaf_rn(__fmul_rn(wyb, wxr[k]), u8_to_f32(__ldg(r1 + xl[k] + 1)), acc);
-            packed |= (__float2uint_rz(acc) & 0xFFu) << (8 * k);
+            // trunc(acc) for 0 <= acc < 256 = the low mantissa byte of RZ(acc + 2^23): an FADD instead of F2I (quarter-rate pipe)
+            packed |= (__float_as_uint(__fadd_rz(acc, 8388608.0f)) & 0xFFu) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(dst + (size_t)y * lv.pitch) = packed;
     }

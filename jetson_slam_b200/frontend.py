@@ -83,6 +83,8 @@ def lib():
         L.jsfe_pack_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_get_keypoints.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_pack_keypoints_once.argtypes = [vp, C.c_int, vp, vp, C.POINTER(C.c_int32), vp]
+        L.jsfe_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t, C.c_int]
+        L.jsfe_host_free.argtypes = [vp]
         L.jsfe_get_stereo.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         L.jsfe_download_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HostResults), vp]
         L.jsfe_process_host_pairs.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(HostResults)]
@@ -134,6 +136,30 @@ def _stream_ptr(stream):
     if hasattr(stream, "cuda_stream"):  # torch.cuda.Stream
         return C.c_void_p(stream.cuda_stream)
     return C.c_void_p(int(stream))
+
+
+class HostBuffer:
+    """Pinned host memory from jsfe_host_alloc as a numpy array (`.array`); write_combined=True for input images the host only
+    writes (the upload is then not snooped through the CPU caches)."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined=False):
+        self._ptr = C.c_void_p()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        _check(lib().jsfe_host_alloc(C.byref(self._ptr), n, int(bool(write_combined))))
+        self.array = np.frombuffer((C.c_uint8 * n).from_address(self._ptr.value), dtype=dtype).reshape(shape)
+        self.write_combined = bool(write_combined)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            lib().jsfe_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Frontend:

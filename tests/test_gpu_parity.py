@@ -249,6 +249,30 @@ def test_batch_slots_are_independent_and_order_invariant():
                 assert np.array_equal(e["depth"][s_, :n].view(np.int32), want["depth"][s_, :n].view(np.int32))
 
 
+@pytest.mark.parametrize("write_combined", [False, True])
+def test_host_buffer_from_the_abi_allocator_feeds_the_host_call(write_combined):
+    """jsfe_host_alloc (cached and write-combined pinned memory) as the `images` buffer of jsfe_process_host_pairs gives the same
+    results as a numpy array, and jsfe_host_free releases it."""
+    cfg = CONFIGS["C1"]
+    pairs = [synth.stereo_pair(cfg.height, cfg.width, 40 + i) for i in range(3)]
+    host = np.stack([im for p in pairs for im in p])
+    fe = frontend.Frontend(**cfg.extractor_kwargs(), max_images=6)
+    want = fe.process_host_pairs(host, cfg.mb, cfg.mbf)
+    want = {k: np.array(v) for k, v in want.items() if k != "bytes"}
+    hb = frontend.HostBuffer(host.shape, np.uint8, write_combined=write_combined)
+    hb.array[...] = host
+    got = fe.process_host_pairs(hb.array, cfg.mb, cfg.mbf)
+    assert np.array_equal(got["n"], want["n"]) and want["n"].min() > 0
+    for s_ in range(6):
+        n = want["n"][s_]
+        assert np.array_equal(got["kps"][s_, :, :n], want["kps"][s_, :, :n]) and np.array_equal(got["desc"][s_, :n], want["desc"][s_, :n])
+        if s_ % 2 == 0:
+            assert np.array_equal(got["u_right"][s_, :n].view(np.int32), want["u_right"][s_, :n].view(np.int32))
+    hb.close()
+    hb.close()      # idempotent
+    fe.close()
+
+
 def test_chunk_schedule_covers_every_pair_exactly_once():
     """jsfe_process_host_pairs for every (chunk_pairs, n_pairs) in 1..4 x 1..16: the ramped schedule (C/4, C/2, C ... C/2, C/4) must
     process exactly the caller's pairs (a schedule that ran past n_pairs would read beyond the host buffer) and give the bytes of
