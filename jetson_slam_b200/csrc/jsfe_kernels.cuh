@@ -172,9 +172,6 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
 //  dense, exact evaluation of the whole tile.
 // =================================================================================================
-#ifndef JSFE_EMIT
-#define JSFE_EMIT 0           // emission loop variant (A/B knob)
-#endif
 #ifndef JSFE_FAST_SWPAD
 #define JSFE_FAST_SWPAD 0     // extra u16 columns per score row: shifts the shared-memory banks from row to row
 #endif
@@ -274,7 +271,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_best[192];
-    __shared__ uint16_t s_codeoff[32];   // emission: code offset of accumulator bit b = (b & 7) * (nrl << 8) + (b >> 3)
     __shared__ unsigned s_ncand;      // work-list counters, packed: bright | dark << 16
     __shared__ int s_npos[8];         // positives per warp (phase C walks a warp's own positives)
     constexpr int PW = JSFE_FAST_PW;
@@ -331,7 +327,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
         for (int i = tid; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
         if (tid < 192) s_best[tid] = 0;
         if (tid == 0) s_ncand = 0;
-        if (tid < 32) s_codeoff[tid] = (uint16_t)((tid & 7) * (lv.fast_nrl << 8) + (tid >> 3));
     }
     __syncthreads();                      // also makes the mbarrier init visible to every thread
     if (p.use_tma) mbar_wait(&s_bar, 0);  // TMA bytes have landed
@@ -419,7 +414,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 int ob = (int)((base & 0xffffu) + (incl & 0xffffu)) - cb;     // first bright slot of this thread
                 int od = (int)((base >> 16) + (incl >> 16)) - cd;            // first dark slot (counted from the back)
                 const int code_base = code_first - (8 - nit) * cstep;
-                // one entry per set bit, highest first
+                // one entry per set bit
                 uint16_t* pb = cand + ob;                 // bright: upwards from the front
                 uint16_t* pd = cand + (cap - 1 - od);     // dark: downwards from the back
                 // a list that does not fit is never read (the counters still say so): keep the stores inside the array
@@ -427,27 +422,14 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
                 if (od + cd > cap) ada = adb = 0;
                 auto emit = [&](unsigned m, int col_off, uint16_t*& ptr, int dir) {
                     const int cb0 = code_base + col_off;
-#if JSFE_EMIT == 0
-                    while (m) {
-                        unsigned b;
-                        asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));        // index of the highest set bit (FLO)
-                        m ^= 1u << b;
-                        *ptr = (uint16_t)(cb0 + s_codeoff[b]);
-                        ptr += dir;
-                    }
-#else
-                    // lowest set bit first: the loop-carried chain is m &= m - 1 (two ALU ops), the bit index is off it
+                    // lowest set bit first: the loop-carried chain is m &= m - 1, the bit index and its code offset
+                    // (b & 7) rows of nrl, (b >> 3) columns are off it
                     while (m) {
                         const unsigned b = (unsigned)__ffs((int)m) - 1u;
                         m &= m - 1u;
-#if JSFE_EMIT == 1
                         *ptr = (uint16_t)(cb0 + (int)imad(b & 7u, (unsigned)cstep, b >> 3));
-#else
-                        *ptr = (uint16_t)(cb0 + s_codeoff[b]);
-#endif
                         ptr += dir;
                     }
-#endif
                 };
                 emit(aba, 0, pb, 1);
                 emit(abb, 4, pb, 1);
@@ -589,6 +571,9 @@ __global__ void __launch_bounds__(256) k_fast_cells(const __grid_constant__ Para
 #ifndef JSFE_BLUR_ROWS
 #define JSFE_BLUR_ROWS 32
 #endif
+#ifndef JSFE_BLUR_BLOCKS
+#define JSFE_BLUR_BLOCKS 3        // resident blocks per SM the register allocation aims at
+#endif
 #define JSFE_FIX_LIST 2048        // block-wide list of ambiguous pixels; beyond it (flat regions) the owner decides its pixels in place
 
 // separable factors of the 7x7 weights; the same for every handle (sigma is fixed at 10 in the reference), kept in
@@ -611,7 +596,7 @@ __device__ __forceinline__ float byte_f(unsigned w, unsigned sel) {   // exact u
     return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
 }
 
-__global__ void __launch_bounds__(256, 3) k_blur(const __grid_constant__ Params p, int slot0) {
+__global__ void __launch_bounds__(256, JSFE_BLUR_BLOCKS) k_blur(const __grid_constant__ Params p, int slot0) {
     __shared__ __align__(16) uint8_t s_flag[256 * JSFE_BLUR_ROWS];   // [thread][row of its strip]: 4-bit ambiguity mask of its 4 pixels
     __shared__ unsigned s_list[JSFE_FIX_LIST];                       // level << 28 | y << 14 | x
     __shared__ int s_n;
