@@ -184,7 +184,7 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
                                   float mb, float mbf);
 int jsfe_process_host_pairs_end(jsfe_handle* h, jsfe_host_results* out);
 /* Pinned host memory for the `images` argument above (what SyncedMem's cudaMallocHost does in the reference,
- * include/cuda/synced_mem_holder.hpp).  write_combined != 0 allocates it cudaHostAllocWriteCombined: the copy engine's reads are
+ * src/cuda/synced_mem_holder.cpp:46,65).  write_combined != 0 allocates it cudaHostAllocWriteCombined: the copy engine's reads are
  * then not snooped through the CPU caches, which is worth ~5 % of host-to-host throughput once several GPUs of one socket upload
  * at the same time (bench.py, 4 GPUs: 184 k -> 193 k pairs/s).  Write-combined memory is for buffers the host only WRITES
  * (a capture / decode target); host reads of it are slow.  Free with jsfe_host_free. */
@@ -304,8 +304,9 @@ int jsfe_cvt_gray(const uint8_t* src, int h, int w, int64_t src_pitch, int chann
  * batch is requested", BASELINE config C5).  The reference has no counterpart (one device, src/cuda/orb_gpu.cpp:24).
  * One process per GPU; each rank owns a handle and a jsfe_gather bound to it.  jsfe_gather_begin packs the results of pairs
  * [first_pair, first_pair + n_pairs) -- trimmed to their keypoint counts -- into ONE region and moves it to the root on the gather's
- * own stream, ordered after `compute_stream`; `compute_stream` is made to wait only for the local packing (tens of microseconds), so
- * the transfer overlaps the next extraction.  Transport: if the non-root ranks mapped the root's landing buffers (CUDA IPC:
+ * own stream, ordered after `compute_stream`.  Nothing is made to wait at this point: the next call that overwrites this handle's
+ * results (jsfe_extract, jsfe_stereo_match*, jsfe_process_host_pairs*) first waits, on the device, for the local packing (tens of
+ * microseconds), so the transfer overlaps the following extraction and work of OTHER handles queued on the same stream is not held up.  Transport: if the non-root ranks mapped the root's landing buffers (CUDA IPC:
  * jsfe_gather_ipc_export on the root, jsfe_gather_ipc_import everywhere else, jsfe_gather_set_peers_mapped(root, 1)), a copy kernel
  * stores the trimmed region straight into the root's memory over NVLink and NCCL only carries two 4-byte all-reduces (double-buffer
  * credit in front of the stores, completion behind them); otherwise the regions travel as one ncclSend/ncclRecv group, padded to

@@ -105,6 +105,9 @@ struct jsfe_handle {
     cudaStream_t st_aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int overlap_blur = 1;
+    // jsfe_gather_begin packs this handle's results on its own stream; the next call that overwrites results waits for this event
+    // first (deferred, so that the caller's stream is not stalled while OTHER handles still have work to run on it)
+    cudaEvent_t pack_pending = nullptr;
     bool pdl = true;      // programmatic dependent launch between the kernels of the chain (JSFE_NO_PDL=1: plain launches)
     uint8_t* d_stage = nullptr;
     cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
@@ -672,9 +675,20 @@ int jsfe_slot_image(jsfe_handle* h, int slot, uint8_t** dev_ptr, int64_t* pitch)
 
 static int extract_chunk(jsfe_handle* h, int first_slot, int n, void* stream);
 
+// results of this handle are about to be overwritten on `st`: a gather's pack of the previous results has to be through
+static int wait_pending_pack(jsfe_handle* h, cudaStream_t st) {
+    if (h->pack_pending) {
+        cudaEvent_t e = h->pack_pending;
+        h->pack_pending = nullptr;
+        if (cudaStreamWaitEvent(st, e, 0) != cudaSuccess) return fail(JSFE_ERR_CUDA, "waiting for the gather's pack failed");
+    }
+    return JSFE_OK;
+}
+
 int jsfe_extract(jsfe_handle* h, int first_slot, int n, void* stream) {
     int rc = check_slots(h, first_slot, n);
     if (rc) return rc;
+    if ((rc = wait_pending_pack(h, (cudaStream_t)stream))) return rc;
     // Large batches are cut into sub-batches whose pyramid + blurred pyramid stay L2-resident between kernels
     // (126 MB L2): the levels written by k_pyramid are then read by k_fast_cells / k_blur / k_orient_desc from L2.
     const int chunk = h->chunk_images > 0 ? h->chunk_images : n;
@@ -770,6 +784,7 @@ int jsfe_stereo_match(jsfe_handle* h, int first_pair, int n, int th_high, int th
     if (n == 0) return JSFE_OK;
     if (!(mb > 0.0f) || th_high < 0 || th_high > 32767) return fail(JSFE_ERR_INVALID, "bad stereo parameters");
     CU(cudaSetDevice(h->device));
+    if ((rc = wait_pending_pack(h, (cudaStream_t)stream))) return rc;
     return launch_stereo(h, right_side_of(h, 2, 0, 2, 1), first_pair, n, th_high, th_low, mb, mbf, (cudaStream_t)stream);
 }
 
@@ -786,6 +801,7 @@ int jsfe_stereo_match_cross(jsfe_handle* hl, int slot_l, jsfe_handle* hr, int sl
                A.lv[i].slot_stride == B.lv[i].slot_stride && A.lv[i].tile_h == B.lv[i].tile_h && A.lv[i].tile_w == B.lv[i].tile_w;
     if (!same) return fail(JSFE_ERR_INVALID, "left and right handles must share device and geometry");
     CU(cudaSetDevice(hl->device));
+    if ((rc = wait_pending_pack(hl, (cudaStream_t)stream))) return rc;
     return launch_stereo(hl, right_side_of(hr, 0, slot_l, 0, slot_r), 0, 1, th_high, th_low, mb, mbf, (cudaStream_t)stream);
 }
 
@@ -983,6 +999,7 @@ int jsfe_process_host_pairs_begin(jsfe_handle* h, int n_pairs, const uint8_t* im
         }
         h->pipe_ready = true;
     }
+    if ((rc = wait_pending_pack(h, h->st_comp))) return rc;
     if (chunk_pairs < 1) chunk_pairs = 32;
     // chunk schedule: a short first chunk (C/4, then C/2) so that compute starts early, full chunks after, and a short
     // last chunk (C/2, C/4) so that little D2H is left when compute ends
@@ -1354,6 +1371,7 @@ int jsfe_gather_destroy(jsfe_gather* g) {
     if (!g) return JSFE_OK;
     cudaSetDevice(g->h->device);
     if (g->st) cudaStreamSynchronize(g->st);
+    if (g->h->pack_pending == g->ev_packed) g->h->pack_pending = nullptr;   // the pack is through
     for (int b = 0; b < 2; ++b) {
         if (g->peer[b]) cudaIpcCloseMemHandle(g->peer[b]);
         if (g->landing[b]) cudaFree(g->landing[b]);
@@ -1441,7 +1459,7 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
     jsfe::k_gather_pack<<<2 * n_pairs, 256, 0, g->st>>>(h->P, first_pair, n_pairs, g->rank, g->seq, region);
     if ((rc = post_launch(h, "k_gather_pack"))) return rc;
     CU(cudaEventRecord(g->ev_packed, g->st));
-    CU(cudaStreamWaitEvent(cs, g->ev_packed, 0));      // the results may be overwritten once they are packed
+    h->pack_pending = g->ev_packed;   // the results may be overwritten once they are packed: the next extraction / match waits for it
     if (g->world > 1) {
         const size_t bound = jsfe::gather_header_bytes(n_pairs) + (size_t)n_pairs * (jsfe::gather_slot_bytes(h->P.cap, 1) + jsfe::gather_slot_bytes(h->P.cap, 0));
         // every rank uses the same transport: the peer mappings are made on all non-root ranks or on none (the root is told with
