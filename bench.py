@@ -676,6 +676,22 @@ def run_ours(args, cfg):
         wall = max_over_ranks((time.perf_counter() - t0) * 1e3)       # includes the last transfers (nothing left in flight)
         barrier()
         gval = world * B * args.steps / (wall / 1e3)
+        # where a gather's time goes on its own stream (all of it overlaps the next extraction): stage times of 8 more steps per rank
+        for g in gs:
+            g.profile(True)
+        acc = np.zeros(4)
+        nprof = 8
+        for k in range(nprof + 2):
+            step_gather(k)
+            if k >= 2:
+                acc += np.array(list(gs[k % 2].stage_times().values()))   # of the gather end() just returned (batch k-2)
+        drain(nprof + 2)
+        for g in gs:
+            g.profile(False)
+        st_t = torch.tensor(acc / nprof, device="cuda", dtype=torch.float64)
+        st_all = [torch.zeros_like(st_t) for _ in range(world)]
+        dist.all_gather(st_all, st_t)
+        st_all = np.stack([t.cpu().numpy() for t in st_all])
         last = gs[(args.steps - 1) % 2].last
         payload = None
         if rank == 0:
@@ -685,6 +701,10 @@ def run_ours(args, cfg):
             assert u["rank"] == world - 1 and u["n_pairs"] == B
         gather_info = {"value": gval, "unit": UNIT, "efficiency_vs_no_gather": gval / value, "ms_per_step": wall / args.steps,
                        "transport": gs[0].transport, "bytes_per_rank_per_step": payload,
+                       "stages_us": {"stages": list(jd.Gatherer.STAGES), "root": [round(float(x), 1) for x in st_all[0]],
+                                     "max_over_ranks": [round(float(x), 1) for x in st_all.max(axis=0)],
+                                     "how": "CUDA events on each rank's gather stream (jsfe_gather_profile), mean of %d gathers; the credit "
+                                            "all-reduce ends when the slowest rank has joined" % nprof},
                        "how": "extract + match + jsfe_gather_begin per step, alternating two handles (batch k is packed and stored into rank 0's "
                               "memory on the gather stream while batch k+1 is extracted); wall clock incl. the final transfers, max over ranks"}
         for g in gs:

@@ -333,6 +333,12 @@ int jsfe_gather_ipc_import(jsfe_gather* g, int buffer /* 0 | 1 */, const uint8_t
 int jsfe_gather_set_peers_mapped(jsfe_gather* g, int all_mapped);
 int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute_stream);
 int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out); /* waits for the gather started by jsfe_gather_begin */
+/* Optional stage timing of this rank's side of a gather (CUDA events on the gather's stream).  After jsfe_gather_profile(g, 1) every
+ * jsfe_gather_begin is timed; jsfe_gather_stage_times gives, for the gather jsfe_gather_end returned last, microseconds of
+ *   [0] the local pack, [1] the credit all-reduce (it ends when the SLOWEST rank has joined: rank skew shows up here),
+ *   [2] the peer-memory stores (non-root ranks; NCCL transport: the send/recv group), [3] the completion all-reduce. */
+int jsfe_gather_profile(jsfe_gather* g, int enable);
+int jsfe_gather_stage_times(jsfe_gather* g, float us[4]);
 int jsfe_gather_destroy(jsfe_gather* g);
 
 /* Stage inspection for tests (device -> host, synchronous): level image, candidate cells, level keypoints. */

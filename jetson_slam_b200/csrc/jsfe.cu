@@ -1359,6 +1359,10 @@ struct jsfe_gather {
     long long seq = 0;
     int last_pairs = 0, in_flight = 0;
     bool peer_all_mapped = false;       // root: every other rank writes its region through a peer mapping (no NCCL receive posted)
+    // optional stage timing (jsfe_gather_profile): events on the gather stream in front of the pack and behind every stage
+    bool timing = false;
+    cudaEvent_t ev_t[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
+    int last_ended = -1;                // buffer of the last gather jsfe_gather_end returned
 };
 
 int64_t jsfe_gather_region_bytes(const jsfe_handle* h, int max_pairs) {
@@ -1376,6 +1380,8 @@ int jsfe_gather_destroy(jsfe_gather* g) {
         if (g->peer[b]) cudaIpcCloseMemHandle(g->peer[b]);
         if (g->landing[b]) cudaFree(g->landing[b]);
         if (g->ev_done[b]) cudaEventDestroy(g->ev_done[b]);
+        for (cudaEvent_t e : g->ev_t[b])
+            if (e) cudaEventDestroy(e);
     }
     if (g->stage) cudaFree(g->stage);
     if (g->token) cudaFree(g->token);
@@ -1400,7 +1406,12 @@ int jsfe_gather_create(jsfe_handle* h, void* nccl_comm, int rank, int world, int
     if (!g) return fail(JSFE_ERR_INVALID, "out of host memory");
     g->h = h; g->comm = (jsfe_nccl_comm_t)nccl_comm; g->rank = rank; g->world = world; g->root = root; g->max_pairs = max_pairs;
     g->region_bytes = (size_t)jsfe_gather_region_bytes(h, max_pairs);
-    cudaError_t e = cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking);
+    // highest priority: the pack, the stores and NCCL's small kernels take the first block slots that free up instead of queueing
+    // behind the whole grid of the extraction kernel that runs beside them (measured: pack 530 -> see DESIGN.md section 8)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = getenv("JSFE_GATHER_NO_PRIORITY") ? cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking)
+                                                      : cudaStreamCreateWithPriority(&g->st, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_packed, cudaEventDisableTiming);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&g->ev_done[b], cudaEventDisableTiming);
@@ -1454,11 +1465,14 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
     const bool p2p = !is_root && g->peer[0] && g->peer[1];
     CU(cudaEventRecord(g->ev_ready, cs));
     CU(cudaStreamWaitEvent(g->st, g->ev_ready, 0));
+    auto mark = [&](int i) { return g->timing ? cudaEventRecord(g->ev_t[b][i], g->st) : cudaSuccess; };
+    CU(mark(0));
     // pack in local HBM (the root: straight into its own region of the landing buffer)
     uint8_t* region = is_root ? g->landing[b] + (size_t)g->rank * g->region_bytes : g->stage;
     jsfe::k_gather_pack<<<2 * n_pairs, 256, 0, g->st>>>(h->P, first_pair, n_pairs, g->rank, g->seq, region);
     if ((rc = post_launch(h, "k_gather_pack"))) return rc;
     CU(cudaEventRecord(g->ev_packed, g->st));
+    CU(mark(1));
     h->pack_pending = g->ev_packed;   // the results may be overwritten once they are packed: the next extraction / match waits for it
     if (g->world > 1) {
         const size_t bound = jsfe::gather_header_bytes(n_pairs) + (size_t)n_pairs * (jsfe::gather_slot_bytes(h->P.cap, 1) + jsfe::gather_slot_bytes(h->P.cap, 0));
@@ -1469,11 +1483,13 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
             // credit: the root joins this all-reduce in ITS jsfe_gather_begin of this batch, i.e. after its consumer released the landing
             // buffer of two batches ago -- no rank stores into that buffer earlier
             NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
+            CU(mark(2));
             if (!is_root) {
                 const int blocks = (int)std::min<size_t>((bound / 16 + 255) / 256, 148 * 8);
                 jsfe::k_gather_put<<<blocks, 256, 0, g->st>>>(g->stage, g->peer[b] + (size_t)g->rank * g->region_bytes, n_pairs);
                 if ((rc = post_launch(h, "k_gather_put"))) return rc;
             }
+            CU(mark(3));
             // completion: behind this all-reduce every rank's stores of this batch have been performed (kernel completion makes them
             // visible system-wide), so the root may read all regions
             NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
@@ -1487,8 +1503,14 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
                 NC(g_nccl.Send(g->stage, bound, 1 /* ncclUint8 */, g->root, g->comm, g->st));
             }
             NC(g_nccl.GroupEnd());
+            CU(mark(2));
+            CU(mark(3));
         }
+    } else {
+        CU(mark(2));
+        CU(mark(3));
     }
+    CU(mark(4));
     CU(cudaEventRecord(g->ev_done[b], g->st));
     g->last_pairs = n_pairs;
     g->in_flight = 1;
@@ -1503,6 +1525,7 @@ int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out) {
     const int b = (int)((g->seq - 1) & 1);
     g->in_flight = 0;
     CU(cudaEventSynchronize(g->ev_done[b]));
+    g->last_ended = b;
     const bool is_root = g->rank == g->root;
     out->data = is_root ? g->landing[b] : nullptr;
     out->region_stride = (int64_t)g->region_bytes;
@@ -1510,6 +1533,31 @@ int jsfe_gather_end(jsfe_gather* g, jsfe_gathered* out) {
     out->root = g->root;
     out->n_pairs = g->last_pairs;
     out->transport = g->world == 1 ? 0 : (is_root ? (g->peer_all_mapped ? 1 : 2) : ((g->peer[0] && g->peer[1]) ? 1 : 2));
+    return JSFE_OK;
+}
+
+int jsfe_gather_profile(jsfe_gather* g, int enable) {
+    if (!g) return fail(JSFE_ERR_INVALID, "null gather");
+    if (g->in_flight) return fail(JSFE_ERR_INVALID, "a gather is in flight");
+    CU(cudaSetDevice(g->h->device));
+    if (enable)
+        for (int b = 0; b < 2; ++b)
+            for (cudaEvent_t& e : g->ev_t[b])
+                if (!e) CU(cudaEventCreate(&e));
+    g->timing = enable != 0;
+    g->last_ended = -1;
+    return JSFE_OK;
+}
+
+int jsfe_gather_stage_times(jsfe_gather* g, float us[4]) {
+    if (!g || !us) return fail(JSFE_ERR_INVALID, "bad argument");
+    if (!g->timing || g->last_ended < 0) return fail(JSFE_ERR_INVALID, "no timed gather has ended (jsfe_gather_profile, then begin/end)");
+    CU(cudaSetDevice(g->h->device));
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, g->ev_t[g->last_ended][i], g->ev_t[g->last_ended][i + 1]));
+        us[i] = ms * 1000.0f;
+    }
     return JSFE_OK;
 }
 

@@ -121,6 +121,19 @@ class Gatherer:
         self.last = g
         return g if self.rank == self.root else None
 
+    STAGES = ("pack", "credit_allreduce", "put", "completion_allreduce")
+
+    def profile(self, on=True):
+        """Time the stages of every following gather on its own stream (jsfe_gather_profile)."""
+        self._chk(self._L.jsfe_gather_profile(self._g, int(bool(on))))
+
+    def stage_times(self) -> dict:
+        """Microseconds per stage of the gather `end()` returned last (this rank's side)."""
+        import ctypes as C
+        us = (C.c_float * 4)()
+        self._chk(self._L.jsfe_gather_stage_times(self._g, us))
+        return {k: float(us[i]) for i, k in enumerate(self.STAGES)}
+
     def regions_to_host(self, g) -> list[np.ndarray]:
         """Root: copy every rank's region (header + payload only) to the host."""
         out = []

@@ -118,6 +118,8 @@ def lib():
         L.jsfe_gather_ipc_export.argtypes = [vp, C.c_int, vp]
         L.jsfe_gather_ipc_import.argtypes = [vp, C.c_int, vp]
         L.jsfe_gather_set_peers_mapped.argtypes = [vp, C.c_int]
+        L.jsfe_gather_profile.argtypes = [vp, C.c_int]
+        L.jsfe_gather_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
         L.jsfe_gather_begin.argtypes = [vp, C.c_int, C.c_int, vp]
         L.jsfe_gather_end.argtypes = [vp, C.POINTER(Gathered)]
         L.jsfe_gather_destroy.argtypes = [vp]
