@@ -1485,7 +1485,10 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
             NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
             CU(mark(2));
             if (!is_root) {
-                const int blocks = (int)std::min<size_t>((bound / 16 + 255) / 256, 148 * 8);
+                // a few blocks are enough (the stores only have to be through within a step) and, on the high-priority stream, all
+                // that may be taken from the extraction running beside them: with 148 x 8 blocks the stores of seven ranks into one
+                // root held every SM of every rank for 0.3 ms per step (8 GPUs: gather efficiency 0.93 instead of 0.96)
+                const int blocks = (int)std::max<size_t>(1, std::min<size_t>((bound / 16 + 255) / 256, 32));
                 jsfe::k_gather_put<<<blocks, 256, 0, g->st>>>(g->stage, g->peer[b] + (size_t)g->rank * g->region_bytes, n_pairs);
                 if ((rc = post_launch(h, "k_gather_put"))) return rc;
             }

@@ -100,7 +100,14 @@ __global__ void __launch_bounds__(256) k_gather_put(const uint8_t* __restrict__ 
     const size_t nvec = bytes >> 4;                       // both terms are multiples of 16
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) d[i] = s[i];
+    // few blocks (the launch takes at most 32): four loads in flight per thread before their stores
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = s[i], b = s[i + stride], c = s[i + 2 * stride], e = s[i + 3 * stride];
+        d[i] = a; d[i + stride] = b; d[i + 2 * stride] = c; d[i + 3 * stride] = e;
+    }
+    for (; i < nvec; i += stride) d[i] = s[i];
 }
 
 }  // namespace jsfe
