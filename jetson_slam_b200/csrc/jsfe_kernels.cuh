@@ -160,17 +160,19 @@ __global__ void __launch_bounds__(256) k_pyramid(const __grid_constant__ Params 
 //            compass points (ring 0,4,8,12) pass -- a necessary condition for any arc the LUT accepts, derived from
 //            FAST_N_MIN and verified against the LUT at create time.  Flags of up to 8 row iterations are kept in
 //            registers (one byte lane per pixel, shifted in from the MSB) and emitted ONCE per thread: warp scan of
-//            the counts, one shared-memory atomic per warp, then a find-leading-one loop.  Bright survivors fill the
+//            the counts, one shared-memory atomic per warp, then a loop over the set bits.  Bright survivors fill the
 //            work list from the front, dark survivors from the back (the position of an entry is its polarity).
 //   phase B  the work list is evaluated densely and EXACTLY for the entry's polarity only: 16 ring bytes packed
 //            4 per word, one packed compare per word, SAD by VABSDIFF4.ACC, the 16 flags merged into one
-//            permuted index of the LUT bitmap.  Hits store their score and go to the positives list.
-//   phase C  the positives list is walked: 3x3 NMS test and one shared-memory atomicMax per cell on a key that
+//            permuted index of the LUT bitmap.  Hits store their score and become positives: a warp writes them
+//            over work-list entries it has already consumed, so the list only has to hold the candidates and is
+//            sized for six resident blocks per SM (LevelGeom::fast_cap).
+//   phase C  every warp walks its positives: 3x3 NMS test and one shared-memory atomicMax per cell on a key that
 //            encodes the reference's tie-break order:
 //            (score desc, column priority of the reference's smem tree asc, y-lane (y-y0)%T asc, y asc).
 //  Every pixel rejected in phase A has score 0 in the reference too; phase B is the reference's arithmetic
-//  (early-outs included), so scores are bit-identical.  Lists that overflow (adversarial images) fall back to a
-//  dense, exact evaluation of the whole tile.
+//  (early-outs included), so scores are bit-identical.  A tile with more survivors than list slots (adversarial
+//  or very textured tiles) falls back to a dense, exact evaluation of the whole tile.
 // =================================================================================================
 #ifndef JSFE_FAST_SWPAD
 #define JSFE_FAST_SWPAD 0     // extra u16 columns per score row: shifts the shared-memory banks from row to row

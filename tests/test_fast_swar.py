@@ -101,3 +101,63 @@ def test_flag_merge_gives_the_permuted_lut_index():
 def test_permutation_is_a_bijection():
     seen = {_index_of_mask(1 << k) for k in range(16)}
     assert seen == {1 << k for k in range(16)}
+
+
+def test_positives_written_over_consumed_entries_never_clobber_an_unread_one():
+    """Phase B of k_fast_cells keeps no separate positives array: warp w evaluates entries [256 it + 32 w, +32) in pass `it` and writes
+    its q-th hit over the (q & 31)-th entry of its (q >> 5)-th pass (bright entries grow from the front of the list, dark ones from
+    the back).  Model of that index arithmetic: every overwritten slot belongs to the writing warp and has been read, and phase C's
+    walk (q-th positive of warp w at entry 256 (q >> 5) + 32 w + (q & 31)) finds exactly the warp's hits in order."""
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        cap = int(rng.integers(1, 3000))
+        ntot = int(rng.integers(0, cap + 1))
+        nb = int(rng.integers(0, ntot + 1))
+        density = rng.choice([0.0, 0.1, 0.4, 0.9, 1.0])
+        hit = rng.random(ntot) < density
+
+        def slot_of(j):
+            return j if j < nb else cap - 1 - (j - nb)
+
+        lst = [None] * cap
+        for j in range(ntot):
+            assert lst[slot_of(j)] is None          # bright and dark entries do not overlap while nb + nd <= cap
+            lst[slot_of(j)] = ("entry", j)
+        read = set()
+        nit = (ntot + 255) >> 8
+        wpos = [0] * 8
+        hits_of = [[] for _ in range(8)]
+        # warps of a block run concurrently: any interleaving is legal as long as a warp-pass reads all its entries before it writes
+        order = [(it, w) for it in range(nit) for w in range(8)]
+        if trial % 2:                               # arbitrary interleaving of the warps; only a warp's own passes stay in order
+            nxt = [0] * 8
+            order = []
+            while len(order) < 8 * nit:
+                w = int(rng.choice([x for x in range(8) if nxt[x] < nit]))
+                order.append((nxt[w], w))
+                nxt[w] += 1
+        for it, w in order:
+            mine = [256 * it + 32 * w + lane for lane in range(32)]
+            codes = {}
+            for i in mine:
+                if i < ntot:
+                    kind, j = lst[slot_of(i)]
+                    assert kind == "entry" and j == i, "an entry was clobbered before it was read"
+                    read.add(i)
+                    codes[i] = j
+            for i in mine:
+                if i < ntot and hit[i]:
+                    q = wpos[w]
+                    wpos[w] += 1
+                    jd = ((q >> 5) << 8) + 32 * w + (q & 31)
+                    assert jd in read and (jd >> 5) & 7 == w and (jd >> 8) <= it
+                    lst[slot_of(jd)] = ("pos", codes[i])
+                    hits_of[w].append(i)
+        for w in range(8):
+            got = []
+            for q in range(wpos[w]):
+                kind, j = lst[slot_of(((q >> 5) << 8) + 32 * w + (q & 31))]
+                assert kind == "pos"
+                got.append(j)
+            assert got == hits_of[w]
+        assert sum(wpos) == int(hit.sum())

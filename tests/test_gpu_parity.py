@@ -99,8 +99,9 @@ def test_other_arc_bands_match_oracle(n_min, n_max, th):
 @pytest.mark.parametrize("cap", [1, 40, 700])
 @pytest.mark.parametrize("kind", ["synthetic", "noise", "checker"])
 def test_fast_list_overflow_paths_stay_exact(cap, kind, monkeypatch):
-    """k_fast_cells keeps its survivors in fixed-size shared-memory lists.  JSFE_DEBUG_FAST_CAP shrinks them so that the overflow
-    paths run (work list: dense evaluation of the tile, both polarities; positives: dense NMS walk); results must not change.
+    """k_fast_cells keeps its survivors in a shared-memory work list sized by jsfe_create (LevelGeom::fast_cap).  JSFE_DEBUG_FAST_CAP
+    shrinks it so that the overflow path runs on most or all tiles (dense evaluation of the tile, both polarities, then the dense NMS
+    walk) and, at cap 700, beside tiles that fit (positives written over consumed entries); results must not change.
     Noise and checkerboard images also put survivors of BOTH polarities next to each other."""
     import dataclasses
     cfg = dataclasses.replace(CONFIGS["C1"], th_fast_max=12)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Regression pins for the adjacent rows: outputs of the oracle restatements on fixed seeded scenes, so that an
 accidental change of the oracle (the checker of the CUDA path) is caught on the CPU.  These are NOT reference outputs: the
-helper kernels are pinned against the reference's kernels on the GPU box (tests/test_helpers.py), f1's host loops are unpinned.
+helper kernels are pinned against the reference's kernels on the GPU box (tests/test_helpers.py), f1's host loops against the
+reference's own host code (tools/make_golden_sbp.py -> tests/golden/sbpref_*.npz).
 usage: python tools/make_golden_adjacent.py"""
 import os
 import sys
