@@ -433,7 +433,7 @@ def run_reference_arm(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(cfg, args.pairs),
+        "config": dict(workload_config(cfg, args.pairs), parallelism=f"{threads} host threads on rank 0, one pair per thread; no GPU"),
         "note": "the reference has no CPU extractor/matcher (SURVEY F2/F3); this arm is the CPU restatement (oracle port) of its CUDA "
                 "path, one pair per host thread, on a bounded sample of the workload",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
