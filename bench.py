@@ -227,16 +227,26 @@ def check_parity(cfg, pairs_seeds, get_pair, golden_dir, n_oracle=2):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
+_CPU_CTX_POOL = {}
+
+
 def cpu_pairs_per_s(cfg, pairs_imgs, threads, pairs_total):
     """Time the oracle (CPU restatement of the reference's path) on `threads` host threads, one stereo pair per task."""
     from oracle import oracle as orc
     import ctypes as C
     kw = cfg.extractor_kwargs()
-    ctxs = [(orc.Oracle(**kw), orc.Oracle(**kw)) for _ in range(threads)]
-    cap = ctxs[0][0].max_kp
-    bufs = [dict(kl=np.zeros(6 * cap, np.int32), dl=np.zeros(32 * cap, np.uint8), kr=np.zeros(6 * cap, np.int32),
-                 dr=np.zeros(32 * cap, np.uint8), ur=np.zeros(cap, np.float32), dp=np.zeros(cap, np.float32),
-                 nr=C.c_int32()) for _ in range(threads)]
+    # per-thread contexts and output buffers are kept across calls: a fresh context is ~20 MB of untouched pages, and first-touch
+    # page faults of 128 threads inside a short timed pass (they serialise on the process's address-space lock) used to make the
+    # port look slower on 64 and 128 threads than on 32
+    pool = _CPU_CTX_POOL.setdefault(cfg.name, [])
+    while len(pool) < threads:
+        ctx = (orc.Oracle(**kw), orc.Oracle(**kw))
+        cap = ctx[0].max_kp
+        pool.append((ctx, dict(kl=np.zeros(6 * cap, np.int32), dl=np.zeros(32 * cap, np.uint8), kr=np.zeros(6 * cap, np.int32),
+                               dr=np.zeros(32 * cap, np.uint8), ur=np.zeros(cap, np.float32), dp=np.zeros(cap, np.float32),
+                               nr=C.c_int32())))
+    ctxs = [p[0] for p in pool[:threads]]
+    bufs = [p[1] for p in pool[:threads]]
     L = orc.lib()
     counter = {"next": 0}
     lock = threading.Lock()
