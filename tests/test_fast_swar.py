@@ -161,3 +161,39 @@ def test_positives_written_over_consumed_entries_never_clobber_an_unread_one():
                 got.append(j)
             assert got == hits_of[w]
         assert sum(wpos) == int(hit.sum())
+
+
+def test_emission_slots_stay_inside_the_list_and_never_overlap_when_it_fits():
+    """Emission of k_fast_cells: every warp reserves (bright, dark) slot counts with ONE packed atomic add (bright | dark << 16),
+    threads take consecutive slots in lane order, bright entries grow from slot 0, dark ones from slot cap - 1 downwards, and a
+    thread whose entries would cross the end of the array writes nothing (the counters still record them, so the block knows the
+    list overflowed and falls back).  Model: all stores are inside [0, cap); if bright + dark <= cap no slot is written twice and
+    exactly bright + dark slots are written."""
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        cap = int(rng.integers(1, 4000))
+        n_chunks = int(rng.integers(1, 12))              # emission rounds of the block (8 warps each)
+        density = rng.choice([0.02, 0.2, 0.6, 1.0])
+        packed = 0                                        # s_ncand
+        written = []
+        for _ in range(n_chunks):
+            for w in rng.permutation(8):                  # the warps' atomics land in any order
+                cb = rng.binomial(64, density * rng.random(), size=32)     # per-lane counts (<= 64 pixels per thread and polarity)
+                cd = rng.binomial(64, density * rng.random(), size=32)
+                inc = np.cumsum(cb) | (np.cumsum(cd) << 16)                # packed inclusive scan (no carry: totals < 65536)
+                tot = int(inc[31])
+                base = packed
+                packed += tot
+                for lane in range(32):
+                    ob = (base & 0xFFFF) + (int(inc[lane]) & 0xFFFF) - int(cb[lane])
+                    od = (base >> 16) + (int(inc[lane]) >> 16) - int(cd[lane])
+                    if ob + cb[lane] <= cap:
+                        written += list(range(ob, ob + int(cb[lane])))
+                    if od + cd[lane] <= cap:
+                        written += [cap - 1 - k for k in range(od, od + int(cd[lane]))]
+            if (packed & 0xFFFF) > 60000 or (packed >> 16) > 60000:
+                break                                      # the kernel's counters are 16 bits: a block has at most 9216 x 2 positions
+        nb, nd = packed & 0xFFFF, packed >> 16
+        assert all(0 <= s < cap for s in written)
+        if nb + nd <= cap:
+            assert len(written) == nb + nd and len(set(written)) == len(written)
