@@ -1498,6 +1498,7 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
             NC(g_nccl.AllReduce(g->token, g->token + 1, 1, 2 /* ncclInt32 */, 0 /* ncclSum */, g->comm, g->st));
         } else {
             // NCCL transport: one send/recv group, padded to the capacity bound (the trimmed size is known on the device only)
+            CU(mark(2));
             NC(g_nccl.GroupStart());
             if (is_root) {
                 for (int r = 0; r < g->world; ++r)
@@ -1506,7 +1507,6 @@ int jsfe_gather_begin(jsfe_gather* g, int first_pair, int n_pairs, void* compute
                 NC(g_nccl.Send(g->stage, bound, 1 /* ncclUint8 */, g->root, g->comm, g->st));
             }
             NC(g_nccl.GroupEnd());
-            CU(mark(2));
             CU(mark(3));
         }
     } else {
